@@ -1,0 +1,369 @@
+#!/usr/bin/env python
+"""bench.py -- K-hop CSR-SpMM propagation throughput on B200 (BASELINE.json metric).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--workload arxiv|products|pubmed|rmatS] [--impl reference]
+
+One "step" = one full pass of the hot path over the workload: the K hops  X -> A^X -> ... -> A^^K X  of the
+normalised adjacency (GraphOp.propagate minus the one-time normalisation, which is reported separately).
+Prints ONE JSON line (contract in the task statement):
+  value     whole-job propagated edges/s = nnz(A^) * K * steps / device time, inputs resident in HBM
+  e2e       same metric through CsrOperator.propagate_host (C ABI sglb200_propagate_host): pinned host X in,
+            K pinned host slabs out, H2D/D2H inside the timed region
+  roofline  achieved algorithmic GB/s of the hop kernel vs the measured HBM peak (MEASURED_PEAKS.json)
+  cpu_baseline  the reference's own CPU kernel (oracle/_ref, compiled from its matmul.c) on this box's host cores
+`--impl reference` times that CPU kernel as the step and prints the same line with "impl": "reference".
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+METRIC = "propagated edges/sec (k-hop SpMM)"
+UNIT = "edges/s"
+
+# shape-matched synthetics of BASELINE.json's configs; the datasets are not available offline
+WORKLOADS = {
+    #            N          directed edges   R-MAT scale  d    K   undirected?
+    "pubmed":   (19_717,    44_324,          15,          500, 3),
+    "arxiv":    (169_343,   1_166_243,       18,          128, 5),
+    "products": (2_449_029, 61_859_140,      22,          100, 6),
+}
+
+
+def parse_args():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--workload", default=None)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--mode", default="fast", choices=["fast", "exact"])
+    ap.add_argument("--tile-items", type=int, default=0)
+    ap.add_argument("--split-threshold", type=int, default=0)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-e2e", action="store_true")
+    return ap.parse_args()
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# synthetic graphs
+# ---------------------------------------------------------------------------------------------------------------
+def rmat_edges(n, m, scale, seed, device):
+    """m directed R-MAT(a=.57, b=.19, c=.19, d=.05) edges on 2^scale ids folded mod n (torch, any device)."""
+    import torch
+    g = torch.Generator(device=device).manual_seed(seed)
+    src = torch.zeros(m, dtype=torch.int64, device=device)
+    dst = torch.zeros(m, dtype=torch.int64, device=device)
+    for _ in range(scale):
+        u = torch.rand(m, generator=g, device=device)
+        src_bit = (u >= 0.76)                                 # quadrants c, d
+        dst_bit = ((u >= 0.57) & (u < 0.76)) | (u >= 0.95)    # quadrants b, d
+        src = (src << 1) | src_bit.to(torch.int64)
+        dst = (dst << 1) | dst_bit.to(torch.int64)
+    # break the bit-pattern locality of raw R-MAT ids with a fixed multiplicative hash, then fold
+    mult = 0x9E3779B1
+    src = ((src * mult) & 0x7FFFFFFF) % n
+    dst = ((dst * mult) & 0x7FFFFFFF) % n
+    return src, dst
+
+
+def build_adjacency(name, device):
+    """scipy CSR (float32, int32) of the symmetrised graph: concatenation without dedup, duplicates summed
+    (reference sgl/data/utils.py:18-24 + sgl/data/base_data.py:29-30)."""
+    import scipy.sparse as sp
+    import torch
+    if name.startswith("rmat"):
+        scale = int(name[4:])
+        n, m, d, K = 1 << scale, 8 << scale, 128, 10
+    else:
+        n, m, scale, d, K = WORKLOADS[name]
+    seed = {"pubmed": 0, "arxiv": 1, "products": 2}.get(name, 4)
+    src, dst = rmat_edges(n, m, scale, seed, device)
+    rows = torch.cat([src, dst])
+    cols = torch.cat([dst, src])
+    keys, counts = torch.unique(rows * n + cols, return_counts=True)   # sorted (row, col), multiplicities
+    rows = torch.div(keys, n, rounding_mode="floor")
+    cols = keys - rows * n
+    indptr = torch.zeros(n + 1, dtype=torch.int64, device=device)
+    indptr[1:] = torch.cumsum(torch.bincount(rows, minlength=n), 0)
+    adj = sp.csr_matrix((counts.to(torch.float32).cpu().numpy(), cols.to(torch.int32).cpu().numpy(),
+                         indptr.cpu().numpy().astype(np.int32 if keys.numel() < 2 ** 31 else np.int64)), shape=(n, n))
+    return adj, d, K
+
+
+def algorithmic_bytes_per_hop(n, nnz, d):
+    """fp32 values + int32 column ids + int64 row pointers, X read once, Y written once."""
+    return 8 * nnz + 8 * (n + 1) + 8 * n * d
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# clocks
+# ---------------------------------------------------------------------------------------------------------------
+class ClockSampler:
+    FIELDS = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+              "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+              "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index=0):
+        self.rows, self.proc, self.gpu = [], None, gpu_index
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.FIELDS}", "--format=csv,noheader,nounits",
+                                          "-lms", "100", "-i", str(self.gpu)], stdout=subprocess.PIPE,
+                                         stderr=subprocess.DEVNULL, text=True)
+            self.thread = threading.Thread(target=self._read, daemon=True)
+            self.thread.start()
+        except OSError:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append((time.perf_counter(), [c.strip() for c in line.split(",")]))
+
+    def stop(self, t0, t1):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        inside = [r for (t, r) in self.rows if t0 <= t <= t1] or [r for (_, r) in self.rows[-3:]]
+        sm, reasons, mx = [], set(), None
+        for r in inside:
+            try:
+                sm.append(float(r[1]))
+                mx = float(r[2])
+            except (ValueError, IndexError):
+                continue
+            for name, val in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), r[4:8]):
+                if val.lower().startswith("active"):
+                    reasons.add(name)
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": mx, "reasons": sorted(reasons),
+                "samples": len(sm)}
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# CPU reference arm
+# ---------------------------------------------------------------------------------------------------------------
+def cpu_reference_steps(adj_norm, x, K, steps, warmup, budget_s=None):
+    """K hops on the host with the reference's own kernel (oracle/_ref/libmatmul_ref.so, built from the reference's
+    matmul.c; falls back to the oracle's C port of the same loop when that build is absent or 32-bit offsets overflow).
+    Returns (seconds per step list, kind, threads)."""
+    from oracle import sgap_oracle as O
+    a = O.Csr(adj_norm.indptr, adj_norm.indices, adj_norm.data, adj_norm.shape)
+    n, d = x.shape
+    ref = O.load_reference_kernel()
+    kind = "reference"
+    if ref is None or n * d >= 2 ** 31 or a.nnz >= 2 ** 31:
+        ref, kind = None, "port"
+    a32 = a.data.astype(np.float32)
+    indptr32 = a.indptr.astype(np.int32) if ref is not None else None
+
+    def one_step():
+        cur = x
+        for _ in range(K):
+            if ref is not None:
+                cur = O.reference_kernel_hop(ref, a, cur, a32, indptr32)
+            else:
+                cur = O.spmm_hop(a, cur, "fma")
+        return cur
+
+    times = []
+    t_begin = time.perf_counter()
+    for i in range(warmup + steps):
+        t0 = time.perf_counter()
+        one_step()
+        dt = time.perf_counter() - t0
+        if i >= warmup:
+            times.append(dt)
+        if budget_s is not None and time.perf_counter() - t_begin > budget_s and times:
+            break
+    return times, kind, O.num_threads()
+
+
+def run_reference(args):
+    import torch
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    name = args.workload or "arxiv"
+    adj, d, K = build_adjacency(name, "cuda" if torch.cuda.is_available() else "cpu")
+    from sgl_b200.operators.utils import adj_to_symmetric_norm
+    adj_norm = adj_to_symmetric_norm(adj, 0.5).tocsr()
+    n, nnz = adj.shape[0], adj_norm.nnz
+    x = torch.randn(n, d, generator=torch.Generator().manual_seed(0)).numpy()
+    times, kind, threads = cpu_reference_steps(adj_norm, x, K, args.steps, args.warmup, budget_s=240.0)
+    sec = float(np.sum(times))
+    value = nnz * K * len(times) / sec
+    line = {"impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus,
+            "steps": len(times), "warmup": args.warmup, "ms_per_step": 1e3 * sec / len(times),
+            "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": workload_config(name, n, nnz, d, K, args),
+            "cpu_baseline": {"value": value, "unit": UNIT, "cores": threads, "kind": kind,
+                             "sample": f"full workload, {len(times)} steps of K={K} hops, bare kernel (no wrapper copies)"},
+            "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+    print(json.dumps(line))
+
+
+def workload_config(name, n, nnz, d, K, args):
+    return {"workload": f"{name}-shape synthetic R-MAT (BASELINE configs[{ {'pubmed': 0, 'arxiv': 1, 'products': 2}.get(name, 4)}])",
+            "N": n, "nnz": nnz, "d": d, "prop_steps": K, "operator": "LaplacianGraphOp r=0.5",
+            "mode": args.mode, "partition": "single GPU" if args.gpus == 1 else f"1-D row partition x{args.gpus}",
+            "l2": "256 MiB buffer written between timed steps (L2 flush); K+1 slabs + CSR exceed L2"}
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# B200 arm
+# ---------------------------------------------------------------------------------------------------------------
+def run_b200(args):
+    import torch
+    from sgl_b200.operators.graph_op import LaplacianGraphOp
+    from sgl_b200.runtime import CsrOperator
+
+    if args.gpus > 1:
+        from bench_dist import run_dist  # noqa: F401  (multi-GPU leg lives next to the partitioner)
+        return run_dist(args)
+
+    torch.cuda.set_device(0)
+    dev = torch.device("cuda", 0)
+    name = args.workload or "arxiv"
+    t0 = time.perf_counter()
+    adj, d, K = build_adjacency(name, dev)
+    t_gen = time.perf_counter() - t0
+    n = adj.shape[0]
+
+    t0 = time.perf_counter()
+    gop = LaplacianGraphOp(K, r=0.5)
+    adj_norm = gop._construct_adj(adj)
+    t_norm = time.perf_counter() - t0
+    t0 = time.perf_counter()
+    op = CsrOperator.from_scipy(adj_norm, tile_items=args.tile_items, split_threshold=args.split_threshold)
+    torch.cuda.synchronize()
+    t_upload = time.perf_counter() - t0
+    nnz = int(adj_norm.nnz)
+    info = op.info()
+
+    x_host = torch.randn(n, d, generator=torch.Generator().manual_seed(0)).pin_memory()
+    hops = [x_host.to(dev)] + [torch.empty(n, d, device=dev) for _ in range(K)]
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
+    stream = torch.cuda.current_stream()
+
+    def step():
+        for k in range(1, K + 1):
+            op.spmm(hops[k - 1], out=hops[k], mode=args.mode)
+
+    for _ in range(max(args.warmup, 3)):
+        step()
+    torch.cuda.synchronize()
+
+    sampler = ClockSampler(0)
+    sampler.start()
+    time.sleep(0.25)
+    starts = [torch.cuda.Event(enable_timing=True) for _ in range(args.steps)]
+    stops = [torch.cuda.Event(enable_timing=True) for _ in range(args.steps)]
+    torch.cuda.synchronize()
+    wall0 = time.perf_counter()
+    for i in range(args.steps):
+        flush.fill_(i & 0xFF)                # evict the previous step's slabs from L2 (outside the event pair)
+        starts[i].record(stream)
+        step()
+        stops[i].record(stream)
+    torch.cuda.synchronize()
+    wall1 = time.perf_counter()
+    clocks = sampler.stop(wall0, wall1)
+    step_ms = [s.elapsed_time(e) for s, e in zip(starts, stops)]
+    total_s = float(np.sum(step_ms)) / 1e3
+    value = nnz * K * args.steps / total_s
+    hop_s = total_s / (args.steps * K)
+
+    peaks = {}
+    peak_src = "fallback 6650 GB/s (B200_PROFILING.md)"
+    try:
+        peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+        peak_gbs, peak_src = float(peaks["hbm_gbs"]), "MEASURED_PEAKS.json hbm_gbs (measured copy bandwidth)"
+    except Exception:
+        peak_gbs = 6650.0
+    b_alg = algorithmic_bytes_per_hop(n, nnz, d)
+    achieved = b_alg / hop_s / 1e9
+    roofline = {"bound": "hbm", "achieved": achieved, "peak": peak_gbs, "unit": "GB/s", "frac": achieved / peak_gbs,
+                "traffic": None, "kernel": "spmm_flat_kernel<4,1,8>", "algorithmic_bytes_per_launch": b_alg,
+                "gather_bytes_per_launch": nnz * (8 + 4 * d) + n * (8 + 4 * d), "us_per_launch": hop_s * 1e6,
+                "peak_source": peak_src}
+    prof = os.path.join(ROOT, "profiles", "traffic.json")
+    if os.path.exists(prof):
+        try:
+            t = json.load(open(prof))
+            if t.get("workload") == name:
+                roofline["traffic"] = t.get("dram_bytes_per_launch")
+        except Exception:
+            pass
+
+    # ---- parity spot check on the timed buffers: every hop against the oracle on a row sample -------------------
+    from oracle import sgap_oracle as O
+    rng = np.random.default_rng(1)
+    sample = np.sort(rng.choice(n, min(n, 2000), replace=False))
+    sub = adj_norm[sample].astype(np.float32)
+    worst = 0.0
+    for k in range(1, K + 1):
+        ref = np.zeros((sample.size, d), dtype=np.float32)
+        O._lib().oracle_spmm_f32_fma_i64(ref, sub.data, sub.indices.astype(np.int32), sub.indptr.astype(np.int64),
+                                         hops[k - 1].cpu().numpy(), sample.size, d)
+        got = hops[k][torch.from_numpy(sample).to(dev)].cpu().numpy()
+        worst = max(worst, float(np.abs(got - ref).max() / max(np.abs(ref).max(), 1e-30)))
+    assert worst <= 1e-5, f"bench parity check failed: {worst}"
+
+    # ---- end to end through the C ABI with host buffers ----------------------------------------------------------
+    e2e = None
+    if not args.no_e2e:
+        e2e_steps = max(3, min(args.steps, 10))
+        for _ in range(2):
+            op.propagate_host(x_host, K, mode=args.mode, keep="all")
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        for _ in range(e2e_steps):
+            outs = op.propagate_host(x_host, K, mode=args.mode, keep="all")
+        torch.cuda.synchronize()
+        dt = time.perf_counter() - t0
+        e2e = {"value": nnz * K * e2e_steps / dt, "unit": UNIT, "h2d_bytes_per_step": n * d * 4,
+               "d2h_bytes_per_step": K * n * d * 4, "ms_per_step": 1e3 * dt / e2e_steps, "steps": e2e_steps,
+               "api": "CsrOperator.propagate_host -> sglb200_propagate_host (pinned host X in, K pinned host slabs out)"}
+        assert float(np.abs(outs[-1].numpy()[sample] - hops[K][torch.from_numpy(sample).to(dev)].cpu().numpy()).max()) == 0.0
+
+    cpu = None
+    if not args.no_cpu_baseline:
+        times, kind, threads = cpu_reference_steps(adj_norm, x_host.numpy(), K, steps=3, warmup=1, budget_s=25.0)
+        cpu = {"value": nnz * K * len(times) / float(np.sum(times)), "unit": UNIT, "cores": threads, "kind": kind,
+               "sample": f"full workload, {len(times)} steps of K={K} hops after 1 warm-up, bare kernel"}
+
+    launches_per_step = K * (1 + (1 if info["carry_runs"] > 0 and args.mode == "fast" else 0))
+    line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": 1, "steps": args.steps, "warmup": max(args.warmup, 3),
+            "ms_per_step": 1e3 * total_s / args.steps, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
+            "dtype": "f32", "data": "synthetic", "config": workload_config(name, n, nnz, d, K, args), "roofline": roofline,
+            "cpu_baseline": cpu, "e2e": e2e, "clocks": clocks, "gpu_launches": launches_per_step * args.steps,
+            "parity": {"checked": "every hop vs oracle fma chain on 2000 sampled rows", "max_rel_err": worst},
+            "setup": {"generate_s": t_gen, "normalise_host_s": t_norm, "upload_and_schedule_s": t_upload,
+                      "tiles": info["tiles_fast"], "cut_rows": info["carry_runs"], "tile_items": info["tile_items"],
+                      "split_threshold": info["split_threshold"], "bytes_resident": info["bytes_resident"]}}
+    print(json.dumps(line))
+
+
+def main():
+    args = parse_args()
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_b200(args)
+
+
+if __name__ == "__main__":
+    main()

@@ -1,0 +1,160 @@
+/*
+ * sglb200.h -- C ABI of libsglb200.so, the B200 (sm_100a) implementation of PKU-DAIR/SGL's SGAP pre-processing
+ * hot path: K-hop CSR x dense propagation  [X, A^X, ..., A^^K X]  and the cross-hop message aggregation.
+ *
+ * Every entry point is extern "C", takes plain pointers and sizes (no torch / C++ types), returns an int status
+ * (SGLB200_OK == 0) and never throws; sglb200_last_error() returns a thread-local description of the last failure.
+ * Device pointers are ordinary CUDA device addresses (e.g. torch.Tensor.data_ptr()); `stream` is a cudaStream_t
+ * passed as void* (NULL = the legacy default stream).  Calls taking device pointers are asynchronous with respect
+ * to the host; calls taking host pointers return after the result is in host memory.
+ * A graph handle is used by one host thread at a time (the reference path is single threaded).
+ *
+ * Reference interfaces replaced (file:line in PKU-DAIR/SGL @ 69cb3248):
+ *   sgl/operators/csrc/matmul.h:5        void FloatCSRMulDenseOMP(float[],float[],int[],int[],float[],int,int)
+ *   sgl/operators/csrc/cudamatmul.c:28   int  FloatCSRMulDense(float[],int,float[],int[],int[],float[],int,int)
+ *   sgl/operators/utils.py:10-40         csr_sparse_dense_matmul(adj, feature)         -> sglb200_spmm*
+ *   sgl/operators/base_op.py:19-36       GraphOp.propagate(adj, feature)               -> sglb200_propagate*
+ *   sgl/operators/utils.py:76-88         adj_to_symmetric_norm                         -> sglb200_normalize_values
+ *   sgl/operators/message_op/*.py        MessageOp._combine (sum/mean/max/min/concat/weighted/over-smooth)
+ *                                                                                      -> sglb200_aggregate*
+ *   sgl/operators/message_op/learnable_weighted_messahe_op.py:59-101                   -> sglb200_lw_*
+ */
+#ifndef SGLB200_H_
+#define SGLB200_H_
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#if defined(__GNUC__)
+#define SGLB200_API __attribute__((visibility("default")))
+#else
+#define SGLB200_API
+#endif
+
+#define SGLB200_VERSION 100 /* major*10000 + minor*100 + patch -> 0.1.0 */
+
+enum sglb200_status {
+    SGLB200_OK = 0,
+    SGLB200_ERR_INVALID = 1,   /* bad argument (NULL, negative size, unsupported combination) */
+    SGLB200_ERR_CUDA = 2,      /* a CUDA runtime call failed; see sglb200_last_error() */
+    SGLB200_ERR_NO_DEVICE = 3, /* no CUDA device / wrong architecture: this library has NO CPU fallback */
+    SGLB200_ERR_ALLOC = 4
+};
+
+/* where a buffer handed to the library lives */
+enum sglb200_location { SGLB200_HOST = 0, SGLB200_DEVICE = 1 };
+
+/* accumulation-order contract of one hop
+ *   FAST : rows longer than the split threshold are cut into tiles and re-combined in a fixed order
+ *          (deterministic run to run; differs from the reference by fp32 re-association on those rows only)
+ *   EXACT: every output element is ONE sequential fused-multiply-add chain in CSR order starting from 0
+ *          == bit-for-bit the reference's shipped libmatmul.so (matmul.c:23-40 built with -mfma) */
+enum sglb200_mode { SGLB200_MODE_FAST = 0, SGLB200_MODE_EXACT = 1 };
+
+/* cross-hop combiners (reference sgl/operators/message_op/) */
+enum sglb200_agg {
+    SGLB200_AGG_SUM = 0,      /* sum_message_op.py:9-10   left-to-right fp32 sum                         */
+    SGLB200_AGG_MEAN = 1,     /* mean_message_op.py:9-10  sum then one true division by the hop count    */
+    SGLB200_AGG_MAX = 2,      /* max_message_op.py:11-12                                                 */
+    SGLB200_AGG_MIN = 3,      /* min_message_op.py:11-12                                                 */
+    SGLB200_AGG_WEIGHTED = 4, /* simple_weighted_message_op.py:40-56 + utils.py:91-102  acc += y_k * w_k */
+    SGLB200_AGG_CONCAT = 5,   /* concat_message_op.py:11-12  hstack into [N, n_feats*d]                  */
+    SGLB200_AGG_OSD = 6       /* over_smooth_distance_op.py:11-33  NAFS cosine-softmax hop weights       */
+};
+
+typedef struct sglb200_graph *sglb200_graph_t;
+
+/* ---- library / device ------------------------------------------------------------------------------------- */
+SGLB200_API int sglb200_version(void);
+SGLB200_API const char *sglb200_last_error(void);
+/* number of visible CUDA devices, or a negative status; fails with SGLB200_ERR_NO_DEVICE when none */
+SGLB200_API int sglb200_device_count(void);
+/* selects `device`, checks compute capability 10.x; every later call on this thread uses it */
+SGLB200_API int sglb200_set_device(int device);
+
+/* ---- graph handle: CSR operator resident in HBM -------------------------------------------------------------
+ * A is n_rows x n_cols (n_rows != n_cols is allowed: a row partition of a larger operator).
+ * indptr: n_rows+1 entries, int32 when indptr_is64 == 0 else int64 (nnz >= 2^31 needs int64);
+ * indices: nnz int32 column ids; vals: nnz float32 (the normalised weights A^_ij, cast once -- the reference
+ * re-casts float64 -> float32 every hop, utils.py:32).  `loc` says whether the three arrays are host or device
+ * memory; they are copied, the caller keeps ownership.  The handle owns the CSR copy, the tile schedules and a
+ * small workspace that grows with the largest feature width seen.
+ * tile_items: merge-path items (rows + non-zeros) per warp, 0 = default; split_threshold: rows with at most
+ * this many non-zeros are never cut across warps in FAST mode, 0 = default. */
+SGLB200_API int sglb200_graph_create(sglb200_graph_t *out, int64_t n_rows, int64_t n_cols, int64_t nnz, const void *indptr,
+                         int indptr_is64, const int32_t *indices, const float *vals, int loc, int tile_items,
+                         int split_threshold, void *stream);
+SGLB200_API int sglb200_graph_destroy(sglb200_graph_t g);
+/* replaces the nnz float32 values of an existing handle (same structure, e.g. another r / alpha) */
+SGLB200_API int sglb200_graph_set_values(sglb200_graph_t g, const float *vals, int loc, void *stream);
+/* info[0]=n_rows [1]=n_cols [2]=nnz [3]=tiles(FAST) [4]=carry runs(FAST) [5]=tiles(EXACT) [6]=tile_items
+ * [7]=split_threshold [8]=bytes resident */
+SGLB200_API int sglb200_graph_info(sglb200_graph_t g, int64_t info[9]);
+
+/* ---- a4: degree normalisation (utils.py:76-88, ppr_graph_op.py:19) -------------------------------------------
+ * Given the structure of A^ = (A+I)^T already in the handle with raw weights w (= (A+I)[j,i] stored at (i,j)) in
+ * raw_w (device or host, nnz float64) and the float64 vectors d_left = deg^(r-1), d_right = deg^(-r)
+ * (n entries each), writes vals[i,j] = fl32( (1-alpha) * fl64(fl64(w * d_left[i]) * d_right[j]) + alpha*[i==j] )
+ * into the handle (alpha == 0 skips the PPR step exactly like LaplacianGraphOp).  All arithmetic is IEEE float64
+ * on the device in the reference's product order, so the float32 values equal the reference's bit for bit. */
+SGLB200_API int sglb200_normalize_values(sglb200_graph_t g, const double *raw_w, const double *d_left, const double *d_right,
+                             double alpha, int apply_ppr, int loc, void *stream);
+
+/* ---- a5/a6/a7: one hop  Y = A X  (+ Y_in when accumulate != 0) ----------------------------------------------
+ * X: [n_cols, d] float32 with row stride ldx (elements), Y: [n_rows, d] with row stride ldy; device pointers.
+ * accumulate != 0 reproduces the reference kernel's `answer += ...` semantics (matmul.c:36-37): each chain
+ * starts from the value already in Y. */
+SGLB200_API int sglb200_spmm(sglb200_graph_t g, const float *X, int64_t ldx, float *Y, int64_t ldy, int d, int mode,
+                 int accumulate, void *stream);
+
+/* ---- a1: K hops, device resident -----------------------------------------------------------------------------
+ * hops[0..K] are K+1 device pointers to [n, d] slabs with row stride ld; hops[0] holds X on entry, hops[k] receives
+ * A^^k X.  Slabs may be column blocks of one [n, (K+1)*d] concat buffer (ld = (K+1)*d).  Requires n_rows==n_cols. */
+SGLB200_API int sglb200_propagate(sglb200_graph_t g, float *const *hops, int64_t ld, int d, int K, int mode, void *stream);
+
+/* same with host buffers: uploads X (host [n,d] contiguous), runs K hops on the device, downloads hop k into
+ * hops_out[k-1] (k = 1..K; NULL entries are skipped, e.g. keep only the last hop).  Synchronous. */
+SGLB200_API int sglb200_propagate_host(sglb200_graph_t g, const float *X, float *const *hops_out, int d, int K, int mode);
+
+/* ---- a8-a10, a13: cross-hop aggregation ----------------------------------------------------------------------
+ * feats: n_feats device pointers to [n, d] slabs (row stride ld_in); out: [n, d] (CONCAT: [n, n_feats*d]) with row
+ * stride ld_out; weights: n_feats float32 on the HOST (WEIGHTED only, else NULL).  The caller applies the
+ * reference's [start:end] slicing by passing only the selected slabs. */
+SGLB200_API int sglb200_aggregate(int op, const float *const *feats, int n_feats, int64_t n, int d, int64_t ld_in,
+                      const float *weights, float *out, int64_t ld_out, void *stream);
+
+/* ---- a11: LearnableWeightedMessageOp, fused forward / backward -----------------------------------------------
+ * kind: 0 simple, 1 simple_allow_neg, 2 gate, 3 ori_ref, 4 jk (learnable_weighted_messahe_op.py:59-86; ori_ref/jk
+ * use the reference's as-written [-1, K'] view of the hop-major score vector).
+ * feats: n_all device pointers [B, d] (all hops, the jk reference row spans all of them); the op combines hops
+ * [start, end).  w: parameter vector on the device (simple: n_all entries; gate: d; ori_ref: 2d; jk: (n_all+1)*d),
+ * bias: 1 float on the device (NULL for simple kinds).  scratch: (end-start)*B floats (scores) + same (weights).
+ * forward writes out [B, d] and keeps the softmax weights in `hop_w` [B, end-start] for the backward. */
+SGLB200_API int sglb200_lw_forward(int kind, const float *const *feats, int n_all, int start, int end, int64_t B, int d,
+                       const float *w, const float *bias, float *hop_w, float *out, void *stream);
+/* backward: grad_out [B, d] -> grad_feats[k] [B, d] for all n_all hops (NULL entries skipped), grad_w (same length as
+ * w, accumulated into: caller zeroes), grad_bias (1 float, accumulated).  scratch: (end-start)*B floats. */
+SGLB200_API int sglb200_lw_backward(int kind, const float *const *feats, int n_all, int start, int end, int64_t B, int d,
+                        const float *w, const float *bias, const float *hop_w, const float *grad_out,
+                        float *const *grad_feats, float *grad_w, float *grad_bias, float *scratch, void *stream);
+
+/* ---- f1: device-resident feature store: out[b, :] = feat[idx[b], :] for every hop in one launch --------------
+ * (models/base_model.py:58-61 does a CPU fancy-index + H2D per step).  idx: B int64 on the device. */
+SGLB200_API int sglb200_gather_rows(const float *const *feats, int n_feats, int64_t ld_in, const int64_t *idx, int64_t B, int d,
+                        float *const *outs, int64_t ld_out, void *stream);
+
+/* ---- legacy ABI: drop-in for the reference's two shared objects ----------------------------------------------
+ * Same symbols, same signatures, host pointers, `answer` is accumulated into (matmul.c:36-37).  Internally:
+ * upload -> EXACT-mode kernel -> download.  int32 offsets as in the reference, but N*d may exceed 2^31. */
+SGLB200_API void FloatCSRMulDenseOMP(float answer[], float data[], int indices[], int indptr[], float mat[], int mat_row,
+                         int mat_col);
+SGLB200_API int FloatCSRMulDense(float answer[], int data_nnz, float data[], int indices[], int indptr[], float mat[],
+                     int mat_row, int mat_col);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* SGLB200_H_ */

@@ -1,0 +1,14 @@
+"""sgl_b200 -- B200-native (sm_100a) SGAP propagate/aggregate path for PKU-DAIR/SGL.
+
+Layout (only what the hot path needs):
+  csrc/        hand-written CUDA kernels + the C ABI (include/sglb200.h) -> libsglb200.so
+  _lib.py      ctypes binding of the C ABI
+  runtime.py   CsrOperator: device-resident CSR handle, K-hop drivers, aggregation launchers
+  operators/   host-side mirror of the reference's sgl.operators (same names, arguments, errors)
+  sgap.py      BaseSGAPModel glue mirror (preprocess / forward contract) + SGC / GAMLP / NAFS style wiring
+  patch.py     install(): routes an importable reference `sgl.operators` through this implementation
+  dist.py      1-D row partition of the operator over the GPUs of one box (torch.distributed / NCCL)
+"""
+from ._lib import SglB200Error  # noqa: F401
+
+__version__ = "0.1.0"

@@ -1,0 +1,475 @@
+// spmm.cu -- the hot path: one hop  Y = A^ X  (CSR x dense, fp32) and the K-hop drivers.
+//
+// Replaces the reference's CPU kernel FloatCSRMulDenseOMP (sgl/operators/csrc/matmul.c:23-40), its ctypes wrapper
+// (sgl/operators/utils.py:10-40) and the hop loop of GraphOp.propagate (sgl/operators/base_op.py:29-36).
+//
+// Kernel shape (B200, sm_100a; the op is a random row gather, ~0.25 flop/byte, HBM/L2 bound):
+//   * merge-path schedule (graph.cu): every warp owns `tile_items` consecutive items of the merged
+//     (row ends + non-zeros) stream, so hubs and empty rows cost the same as anything else -- the reference's
+//     static OpenMP row split (matmul.c:25) serialises on skewed graphs;
+//   * a warp walks its non-zero range as ONE flat stream: 32 (col, val) pairs are fetched with one coalesced
+//     streaming load each, then broadcast by shuffle; all 32 lanes hold disjoint 128-bit column slices of the
+//     same output row, so one warp-wide LDG.128 moves a whole 512 B feature row of X (d = 128);
+//   * U gathered rows are in flight per warp before the first FMA consumes them (memory-level parallelism);
+//   * row boundaries are warp-uniform branches against a shuffle-distributed prefetch of 32 row ends;
+//   * per output element the additions happen in CSR order with one fused multiply-add per term: for rows that
+//     are not cut (all rows in the EXACT schedule) this IS the reference's chain, bit for bit;
+//   * rows cut across warps (FAST schedule, rows longer than split_threshold) leave partial sums in a small
+//     workspace that a second kernel folds in tile order -- deterministic, no atomics.
+#include <limits.h>
+
+#include "common.cuh"
+
+namespace sglb200 {
+
+constexpr int kWarpsPerBlock = 8;
+constexpr unsigned kFull = 0xffffffffu;
+
+struct SpmmParams {
+    const int64_t *indptr;
+    const int32_t *indices;
+    const float *vals;
+    const int32_t *tile_row;
+    const int64_t *tile_nnz;
+    const int32_t *carry_slot;
+    int64_t n_tiles;
+    int64_t n_rows;
+    const float *X;
+    int64_t ldx;
+    float *Y;
+    int64_t ldy;
+    int d;
+    float *carry_ws;
+    int64_t ws_ld;
+};
+
+template <int VEC> struct Vec;
+template <> struct Vec<1> { using type = float; };
+template <> struct Vec<2> { using type = float2; };
+template <> struct Vec<4> { using type = float4; };
+
+// gathered feature rows: read-only path, L1-allocating (hub rows of skewed graphs are re-read by neighbouring warps)
+template <int VEC> __device__ __forceinline__ void load_row_slice(float (&r)[VEC], const float *p)
+{
+    if constexpr (VEC == 4) {
+        const float4 v = __ldg(reinterpret_cast<const float4 *>(p));
+        r[0] = v.x; r[1] = v.y; r[2] = v.z; r[3] = v.w;
+    } else if constexpr (VEC == 2) {
+        const float2 v = __ldg(reinterpret_cast<const float2 *>(p));
+        r[0] = v.x; r[1] = v.y;
+    } else {
+        r[0] = __ldg(p);
+    }
+}
+template <int VEC> __device__ __forceinline__ void load_plain(float (&r)[VEC], const float *p)
+{
+    if constexpr (VEC == 4) {
+        const float4 v = *reinterpret_cast<const float4 *>(p);
+        r[0] = v.x; r[1] = v.y; r[2] = v.z; r[3] = v.w;
+    } else if constexpr (VEC == 2) {
+        const float2 v = *reinterpret_cast<const float2 *>(p);
+        r[0] = v.x; r[1] = v.y;
+    } else {
+        r[0] = *p;
+    }
+}
+template <int VEC> __device__ __forceinline__ void store_slice(float *p, const float (&r)[VEC])
+{
+    if constexpr (VEC == 4) *reinterpret_cast<float4 *>(p) = make_float4(r[0], r[1], r[2], r[3]);
+    else if constexpr (VEC == 2) *reinterpret_cast<float2 *>(p) = make_float2(r[0], r[1]);
+    else *p = r[0];
+}
+// the CSR stream is touched once per hop: keep it out of L1
+__device__ __forceinline__ int32_t load_stream_i32(const int32_t *p)
+{
+    int32_t v;
+    asm volatile("ld.global.nc.L1::no_allocate.s32 %0, [%1];" : "=r"(v) : "l"(p));
+    return v;
+}
+__device__ __forceinline__ float load_stream_f32(const float *p)
+{
+    float v;
+    asm volatile("ld.global.nc.L1::no_allocate.f32 %0, [%1];" : "=f"(v) : "l"(p));
+    return v;
+}
+
+template <int VEC, int VPL, int U, bool ACCUM>
+__global__ void __launch_bounds__(kWarpsPerBlock * 32) spmm_flat_kernel(const SpmmParams p)
+{
+    const int lane = threadIdx.x & 31;
+    const int64_t t = (int64_t)blockIdx.x * kWarpsPerBlock + (threadIdx.x >> 5);
+    if (t >= p.n_tiles) return;
+
+    int64_t row = p.tile_row[t];
+    const int64_t row_end = p.tile_row[t + 1];
+    const int64_t j0 = p.tile_nnz[t];
+    const int n_nnz = (int)(p.tile_nnz[t + 1] - j0);
+
+    // this lane's column slices of the output row
+    const int col_block = blockIdx.y * (32 * VEC * VPL);
+    int cofs[VPL];
+    bool act[VPL];
+#pragma unroll
+    for (int v = 0; v < VPL; ++v) {
+        cofs[v] = col_block + (v * 32 + lane) * VEC;
+        act[v] = cofs[v] < p.d;
+    }
+    float acc[VPL][VEC];
+
+    auto init_acc = [&](int64_t r) {
+#pragma unroll
+        for (int v = 0; v < VPL; ++v) {
+#pragma unroll
+            for (int e = 0; e < VEC; ++e) acc[v][e] = 0.0f;
+            if (ACCUM) {
+                if (act[v] && r < p.n_rows) load_plain<VEC>(acc[v], p.Y + r * p.ldy + cofs[v]);
+            }
+        }
+    };
+
+    // ends (relative to j0) of rows row_base .. row_base+31, one per lane
+    auto load_row_ends = [&](int64_t base) -> int {
+        const int64_t r = base + 1 + lane;
+        if (r > p.n_rows) return INT_MAX;
+        const int64_t rel = p.indptr[r] - j0;
+        return rel > (int64_t)INT_MAX ? INT_MAX : (int)rel;
+    };
+    int64_t row_base = row;
+    int my_end = load_row_ends(row_base);
+    int next_end = __shfl_sync(kFull, my_end, 0);
+
+    if (ACCUM) {
+        // the chain of a row starts from the value already in Y only in the tile that holds the row start
+        const bool starts_here = row < p.n_rows && p.indptr[row] == j0;
+        init_acc(starts_here ? row : p.n_rows);
+    } else {
+        init_acc(p.n_rows);
+    }
+
+    auto flush_row = [&]() {
+        float *yrow = p.Y + row * p.ldy;
+#pragma unroll
+        for (int v = 0; v < VPL; ++v)
+            if (act[v]) store_slice<VEC>(yrow + cofs[v], acc[v]);
+        ++row;
+        if (row - row_base == 32) {
+            row_base = row;
+            my_end = load_row_ends(row_base);
+        }
+        next_end = __shfl_sync(kFull, my_end, (int)(row - row_base));
+        init_acc(row);  // every later row of the tile starts inside the tile
+    };
+
+    const int32_t *cols = p.indices + j0;
+    const float *vals = p.vals + j0;
+
+    for (int base = 0; base < n_nnz; base += 32) {
+        const int n_here = min(32, n_nnz - base);
+        int32_t my_col = 0;
+        float my_val = 0.0f;
+        if (lane < n_here) {
+            my_col = load_stream_i32(cols + base + lane);
+            my_val = load_stream_f32(vals + base + lane);
+        }
+        if (n_here == 32) {
+#pragma unroll
+            for (int k = 0; k < 32; k += U) {
+                float x[U][VPL][VEC];
+#pragma unroll
+                for (int u = 0; u < U; ++u) {
+                    const int32_t c = __shfl_sync(kFull, my_col, k + u);
+                    const float *xrow = p.X + (int64_t)c * p.ldx;
+#pragma unroll
+                    for (int v = 0; v < VPL; ++v) {
+                        if (act[v]) load_row_slice<VEC>(x[u][v], xrow + cofs[v]);
+                        else {
+#pragma unroll
+                            for (int e = 0; e < VEC; ++e) x[u][v][e] = 0.0f;
+                        }
+                    }
+                }
+#pragma unroll
+                for (int u = 0; u < U; ++u) {
+                    const int jj = base + k + u;
+                    while (jj == next_end && row < row_end) flush_row();
+                    const float w = __shfl_sync(kFull, my_val, k + u);
+#pragma unroll
+                    for (int v = 0; v < VPL; ++v)
+#pragma unroll
+                        for (int e = 0; e < VEC; ++e) acc[v][e] = fmaf(w, x[u][v][e], acc[v][e]);
+                }
+            }
+        } else {
+            for (int k = 0; k < n_here; k += U) {
+                float x[U][VPL][VEC];
+#pragma unroll
+                for (int u = 0; u < U; ++u) {
+                    const int32_t c = __shfl_sync(kFull, my_col, (k + u) & 31);
+                    const float *xrow = p.X + (int64_t)c * p.ldx;
+#pragma unroll
+                    for (int v = 0; v < VPL; ++v) {
+                        if (act[v] && k + u < n_here) load_row_slice<VEC>(x[u][v], xrow + cofs[v]);
+                        else {
+#pragma unroll
+                            for (int e = 0; e < VEC; ++e) x[u][v][e] = 0.0f;
+                        }
+                    }
+                }
+#pragma unroll
+                for (int u = 0; u < U; ++u) {
+                    const float w = __shfl_sync(kFull, my_val, (k + u) & 31);
+                    if (k + u < n_here) {
+                        const int jj = base + k + u;
+                        while (jj == next_end && row < row_end) flush_row();
+#pragma unroll
+                        for (int v = 0; v < VPL; ++v)
+#pragma unroll
+                            for (int e = 0; e < VEC; ++e) acc[v][e] = fmaf(w, x[u][v][e], acc[v][e]);
+                    }
+                }
+            }
+        }
+    }
+    // rows (possibly empty ones) that end exactly at the end of the tile
+    while (row < row_end) flush_row();
+    // partial sum of the row cut by the tile end
+    const int32_t slot = p.carry_slot[t];
+    if (slot >= 0) {
+        float *wrow = p.carry_ws + (int64_t)slot * p.ws_ld;
+#pragma unroll
+        for (int v = 0; v < VPL; ++v)
+            if (act[v]) store_slice<VEC>(wrow + cofs[v], acc[v]);
+    }
+}
+
+// folds the carried partial sums of every cut row into Y, in tile order (one warp per cut row)
+template <int VEC>
+__global__ void __launch_bounds__(kWarpsPerBlock * 32)
+    spmm_carry_fixup_kernel(const int32_t *__restrict__ run_row, const int64_t *__restrict__ run_base,
+                            const int32_t *__restrict__ run_len, int64_t n_runs, const float *__restrict__ ws,
+                            int64_t ws_ld, float *__restrict__ Y, int64_t ldy, int d)
+{
+    const int lane = threadIdx.x & 31;
+    const int64_t r = (int64_t)blockIdx.x * kWarpsPerBlock + (threadIdx.x >> 5);
+    if (r >= n_runs) return;
+    const int64_t row = run_row[r];
+    const int64_t base = run_base[r];
+    const int len = run_len[r];
+    for (int c = lane * VEC; c < d; c += 32 * VEC) {
+        float sum[VEC];
+        load_plain<VEC>(sum, ws + base * ws_ld + c);
+        for (int u = 1; u < len; ++u) {
+            float part[VEC];
+            load_plain<VEC>(part, ws + (base + u) * ws_ld + c);
+#pragma unroll
+            for (int e = 0; e < VEC; ++e) sum[e] += part[e];
+        }
+        float y[VEC];
+        load_plain<VEC>(y, Y + row * ldy + c);
+#pragma unroll
+        for (int e = 0; e < VEC; ++e) y[e] += sum[e];
+        store_slice<VEC>(Y + row * ldy + c, y);
+    }
+}
+
+template <int VEC, int VPL, int U>
+static cudaError_t launch_flat(const SpmmParams &p, bool accum, dim3 grid, cudaStream_t stream)
+{
+    if (accum) spmm_flat_kernel<VEC, VPL, U, true><<<grid, kWarpsPerBlock * 32, 0, stream>>>(p);
+    else spmm_flat_kernel<VEC, VPL, U, false><<<grid, kWarpsPerBlock * 32, 0, stream>>>(p);
+    return cudaGetLastError();
+}
+
+static bool aligned(const void *p, size_t a) { return (reinterpret_cast<uintptr_t>(p) % a) == 0; }
+
+// choose the vector width and slices per lane: maximise the used fraction of the 32*VPL lane slots, prefer wide loads
+static void pick_shape(int d, int max_vec, int *vec_out, int *vpl_out, int *col_blocks)
+{
+    double best_util = -1.0;
+    int best_vec = 1, best_vpl = 1;
+    for (int vec = max_vec; vec >= 1; vec >>= 1) {
+        if (d % vec) continue;
+        const int slots_needed = d / vec;
+        int vpl = 1;
+        while (vpl < 4 && 32 * vpl < slots_needed) vpl <<= 1;
+        const int per_block = 32 * vpl;
+        const int blocks = (slots_needed + per_block - 1) / per_block;
+        const double util = (double)slots_needed / ((double)blocks * per_block);
+        if (util > best_util + 1e-9) {
+            best_util = util;
+            best_vec = vec;
+            best_vpl = vpl;
+        }
+    }
+    *vec_out = best_vec;
+    *vpl_out = best_vpl;
+    const int per_block = 32 * best_vpl * best_vec;
+    *col_blocks = (d + per_block - 1) / per_block;
+}
+
+int spmm_launch(sglb200_graph *g, const float *X, int64_t ldx, float *Y, int64_t ldy, int d, int mode, int accumulate,
+                cudaStream_t stream)
+{
+    SGL_REQUIRE(g != nullptr, "spmm: graph is NULL");
+    SGL_REQUIRE(d >= 0, "spmm: negative feature width");
+    if (g->n_rows == 0 || d == 0) return SGLB200_OK;
+    SGL_REQUIRE(X != nullptr && Y != nullptr, "spmm: X or Y is NULL");
+    SGL_REQUIRE(ldx >= d && ldy >= d, "spmm: row stride smaller than the feature width");
+    SGL_REQUIRE(mode == SGLB200_MODE_FAST || mode == SGLB200_MODE_EXACT, "spmm: unknown mode %d", mode);
+    Schedule *s = &g->fast;
+    // accumulate starts every chain from the value already in Y: a cut row would race between the warp that reads
+    // Y_in at the row start and the warp that stores the row end, so accumulation always runs on whole rows.
+    if (mode == SGLB200_MODE_EXACT || accumulate) {
+        if (!g->exact.built) {
+            const int st = build_schedule(g, &g->exact, -1, stream);
+            if (st != SGLB200_OK) return st;
+        }
+        s = &g->exact;
+    }
+    if (s->n_tiles == 0) return SGLB200_OK;
+
+    int max_vec = 4;
+    if (d % 4 || ldx % 4 || ldy % 4 || !aligned(X, 16) || !aligned(Y, 16)) max_vec = 2;
+    if (max_vec == 2 && (d % 2 || ldx % 2 || ldy % 2 || !aligned(X, 8) || !aligned(Y, 8))) max_vec = 1;
+    int vec, vpl, col_blocks;
+    pick_shape(d, max_vec, &vec, &vpl, &col_blocks);
+
+    const int64_t ws_ld = (d + 3) & ~3;
+    if (s->n_slots > 0) {
+        const int st = ensure_carry_ws(g, (size_t)s->n_slots * (size_t)ws_ld);
+        if (st != SGLB200_OK) return st;
+    }
+    SpmmParams p;
+    p.indptr = g->indptr;
+    p.indices = g->indices;
+    p.vals = g->vals;
+    p.tile_row = s->tile_row;
+    p.tile_nnz = s->tile_nnz;
+    p.carry_slot = s->carry_slot;
+    p.n_tiles = s->n_tiles;
+    p.n_rows = g->n_rows;
+    p.X = X;
+    p.ldx = ldx;
+    p.Y = Y;
+    p.ldy = ldy;
+    p.d = d;
+    p.carry_ws = g->carry_ws;
+    p.ws_ld = ws_ld;
+
+    const dim3 grid((unsigned)((s->n_tiles + kWarpsPerBlock - 1) / kWarpsPerBlock), (unsigned)col_blocks, 1);
+    const bool acc = accumulate != 0;
+    cudaError_t e = cudaSuccess;
+#define SGL_SHAPE(V, L, UU) \
+    if (vec == V && vpl == L) e = launch_flat<V, L, UU>(p, acc, grid, stream)
+    SGL_SHAPE(4, 1, 8);
+    else SGL_SHAPE(4, 2, 4);
+    else SGL_SHAPE(4, 4, 2);
+    else SGL_SHAPE(2, 1, 8);
+    else SGL_SHAPE(2, 2, 4);
+    else SGL_SHAPE(2, 4, 2);
+    else SGL_SHAPE(1, 1, 8);
+    else SGL_SHAPE(1, 2, 8);
+    else SGL_SHAPE(1, 4, 4);
+    else {
+        set_error("spmm: no kernel shape for vec=%d vpl=%d", vec, vpl);
+        return SGLB200_ERR_INVALID;
+    }
+#undef SGL_SHAPE
+    SGL_CUDA_CHECK(e);
+    if (s->n_runs > 0) {
+        const unsigned blocks = (unsigned)((s->n_runs + kWarpsPerBlock - 1) / kWarpsPerBlock);
+        if (vec == 4)
+            spmm_carry_fixup_kernel<4><<<blocks, kWarpsPerBlock * 32, 0, stream>>>(
+                s->run_row, s->run_base, s->run_len, s->n_runs, g->carry_ws, ws_ld, Y, ldy, d);
+        else if (vec == 2)
+            spmm_carry_fixup_kernel<2><<<blocks, kWarpsPerBlock * 32, 0, stream>>>(
+                s->run_row, s->run_base, s->run_len, s->n_runs, g->carry_ws, ws_ld, Y, ldy, d);
+        else
+            spmm_carry_fixup_kernel<1><<<blocks, kWarpsPerBlock * 32, 0, stream>>>(
+                s->run_row, s->run_base, s->run_len, s->n_runs, g->carry_ws, ws_ld, Y, ldy, d);
+        SGL_CUDA_CHECK(cudaGetLastError());
+    }
+    return SGLB200_OK;
+}
+
+static int ensure_stage(sglb200_graph *g, size_t floats)
+{
+    if (floats <= g->stage_floats) return SGLB200_OK;
+    SGL_CUDA_CHECK(cudaDeviceSynchronize());
+    for (int k = 0; k < 3; ++k) {
+        cudaFree(g->stage[k]);
+        g->stage[k] = nullptr;
+    }
+    g->bytes_resident -= 3 * g->stage_floats * sizeof(float);
+    g->stage_floats = 0;
+    for (int k = 0; k < 3; ++k) SGL_CUDA_CHECK(cudaMalloc(&g->stage[k], floats * sizeof(float)));
+    g->stage_floats = floats;
+    g->bytes_resident += 3 * floats * sizeof(float);
+    return SGLB200_OK;
+}
+
+}  // namespace sglb200
+
+using namespace sglb200;
+
+extern "C" {
+
+int sglb200_spmm(sglb200_graph_t g, const float *X, int64_t ldx, float *Y, int64_t ldy, int d, int mode,
+                 int accumulate, void *stream)
+{
+    clear_error();
+    return spmm_launch(g, X, ldx, Y, ldy, d, mode, accumulate, (cudaStream_t)stream);
+}
+
+int sglb200_propagate(sglb200_graph_t g, float *const *hops, int64_t ld, int d, int K, int mode, void *stream)
+{
+    clear_error();
+    SGL_REQUIRE(g && hops, "propagate: NULL argument");
+    SGL_REQUIRE(K >= 0, "propagate: negative prop_steps");
+    SGL_REQUIRE(g->n_rows == g->n_cols, "propagate: operator must be square (use sglb200_spmm for row partitions)");
+    for (int k = 1; k <= K; ++k) {
+        SGL_REQUIRE(hops[k] != hops[k - 1], "propagate: hop %d aliases hop %d", k, k - 1);
+        const int st = spmm_launch(g, hops[k - 1], ld, hops[k], ld, d, mode, 0, (cudaStream_t)stream);
+        if (st != SGLB200_OK) return st;
+    }
+    return SGLB200_OK;
+}
+
+int sglb200_propagate_host(sglb200_graph_t g, const float *X, float *const *hops_out, int d, int K, int mode)
+{
+    clear_error();
+    SGL_REQUIRE(g && X, "propagate_host: NULL argument");
+    SGL_REQUIRE(K >= 0 && d >= 0, "propagate_host: negative size");
+    SGL_REQUIRE(g->n_rows == g->n_cols, "propagate_host: operator must be square");
+    SGL_REQUIRE(K == 0 || hops_out != nullptr, "propagate_host: hops_out is NULL");
+    const size_t slab = (size_t)g->n_rows * (size_t)d;
+    if (slab == 0 || K == 0) return SGLB200_OK;
+    {
+        const int st = ensure_stage(g, slab);
+        if (st != SGLB200_OK) return st;
+    }
+    // three device slabs in a ring: hop k is computed into slab k%3 on the compute stream while hop k-1 drains to the
+    // host on the copy stream; slab k%3 is reused only after the download of hop k-3 has finished.
+    cudaStream_t cs = g->copy_stream;  // uploads + downloads
+    cudaStream_t ks = nullptr;         // kernels on the legacy default stream of the caller's thread
+    SGL_CUDA_CHECK(cudaMemcpyAsync(g->stage[0], X, slab * sizeof(float), cudaMemcpyHostToDevice, cs));
+    SGL_CUDA_CHECK(cudaEventRecord(g->ev_copy[0], cs));
+    SGL_CUDA_CHECK(cudaStreamWaitEvent(ks, g->ev_copy[0], 0));
+    for (int k = 1; k <= K; ++k) {
+        const int dst = k % 3, src = (k - 1) % 3;
+        if (k >= 3) SGL_CUDA_CHECK(cudaStreamWaitEvent(ks, g->ev_copy[dst], 0));  // download of hop k-3 done
+        const int st = spmm_launch(g, g->stage[src], d, g->stage[dst], d, d, mode, 0, ks);
+        if (st != SGLB200_OK) return st;
+        SGL_CUDA_CHECK(cudaEventRecord(g->ev_compute[dst], ks));
+        if (hops_out[k - 1]) {
+            SGL_CUDA_CHECK(cudaStreamWaitEvent(cs, g->ev_compute[dst], 0));
+            SGL_CUDA_CHECK(cudaMemcpyAsync(hops_out[k - 1], g->stage[dst], slab * sizeof(float), cudaMemcpyDeviceToHost, cs));
+        }
+        SGL_CUDA_CHECK(cudaEventRecord(g->ev_copy[dst], cs));
+    }
+    SGL_CUDA_CHECK(cudaStreamSynchronize(ks));
+    SGL_CUDA_CHECK(cudaStreamSynchronize(cs));
+    return SGLB200_OK;
+}
+
+}  // extern "C"

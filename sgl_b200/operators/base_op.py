@@ -1,0 +1,98 @@
+"""Mirror of the reference's sgl/operators/base_op.py: GraphOp (K-hop propagation) and MessageOp (aggregation).
+
+GraphOp.propagate   reference base_op.py:19-36  -> CsrOperator (libsglb200: sglb200_graph_create + propagate)
+MessageOp.aggregate reference base_op.py:53-60
+"""
+from __future__ import annotations
+
+import os
+
+import numpy as np
+import scipy.sparse as sp
+import torch
+import torch.nn as nn
+from torch import Tensor
+
+from ..runtime import CsrOperator, require_cuda
+
+
+class GraphOp:
+    """K-hop propagation  [X, A^X, ..., A^^K X]  of a normalised adjacency A^ built by ``_construct_adj``.
+
+    Same contract as the reference (base_op.py:11-36): ``adj`` is a scipy CSR matrix, ``feature`` a float32
+    ``numpy.ndarray`` ([N, d]; a ``torch.Tensor`` is accepted too, which the reference's own callers pass,
+    SURVEY.md section 9), the result is a list of K+1 ``torch.FloatTensor`` whose first element shares memory
+    with ``feature``; ``self._adj`` holds the normalised CSR afterwards.
+
+    B200 specifics, all optional: ``mode`` ("fast" | "exact", class attribute or env SGLB200_MODE) selects the
+    accumulation-order contract of the hop kernel; ``output_device`` ("cpu" | "cuda", env SGLB200_OUTPUT) keeps the
+    K+1 slabs resident in HBM and returns CUDA tensors (``feat[idx].to(device)`` in the caller's forward then is an
+    on-device gather instead of a CPU gather + PCIe copy).
+    """
+
+    mode = os.environ.get("SGLB200_MODE", "fast")
+    output_device = os.environ.get("SGLB200_OUTPUT", "cpu")
+
+    def __init__(self, prop_steps):
+        self._prop_steps = prop_steps
+        self._adj = None
+        self._operator = None  # CsrOperator of the last propagate call (kept for the next hop set on the same graph)
+
+    def _construct_adj(self, adj):
+        raise NotImplementedError
+
+    def propagate(self, adj, feature):
+        self._adj = self._construct_adj(adj)
+
+        if not isinstance(adj, sp.csr_matrix):
+            raise TypeError("The adjacency matrix must be a scipy csr sparse matrix!")
+        elif not isinstance(feature, (np.ndarray, Tensor)):
+            raise TypeError("The feature matrix must be a numpy.ndarray!")
+        elif self._adj.shape[1] != feature.shape[0]:
+            raise ValueError("Dimension mismatch detected for the adjacency and the feature matrix!")
+
+        if isinstance(feature, Tensor):
+            first = feature.detach()
+            first = first if first.dtype == torch.float32 else first.float()
+        else:
+            if feature.dtype != np.float32:
+                # the reference's ctypes signature rejects anything but float32 (utils.py:21-25)
+                raise TypeError("The feature matrix must be a float32 numpy.ndarray!")
+            first = torch.from_numpy(feature)  # shares memory, like torch.FloatTensor(ndarray) at base_op.py:36
+        require_cuda()
+
+        if self._operator is not None:
+            self._operator.close()
+        self._operator = CsrOperator.from_scipy(self._adj)
+
+        if self.output_device == "cuda":
+            hops = self._operator.propagate(first.cuda(), self._prop_steps, mode=self.mode)
+            return hops
+        rest = self._operator.propagate_host(first.cpu(), self._prop_steps, mode=self.mode, keep="all")
+        return [first.cpu()] + rest
+
+
+class MessageOp(nn.Module):
+    """Cross-hop combiner base class (reference base_op.py:40-60)."""
+
+    def __init__(self, start=None, end=None):
+        super(MessageOp, self).__init__()
+        self._aggr_type = None
+        self._start, self._end = start, end
+
+    @property
+    def aggr_type(self):
+        return self._aggr_type
+
+    def _combine(self, feat_list):
+        raise NotImplementedError
+
+    def aggregate(self, feat_list):
+        if not isinstance(feat_list, list):
+            # the reference *returns* the exception object here (base_op.py:55); raising is the evident intent
+            raise TypeError("The input must be a list consists of feature matrices!")
+        for feat in feat_list:
+            if not isinstance(feat, Tensor):
+                raise TypeError("The feature matrices must be tensors!")
+
+        return self._combine(feat_list)

@@ -1,0 +1,138 @@
+"""Learnable cross-hop combiners (reference sgl/operators/message_op/learnable_weighted_messahe_op.py,
+iterate_learnable_weighted_message_op.py, projected_concat_message_op.py).
+
+These run inside ``forward`` on mini-batches that already live on the training device, with autograd.  The weight
+computation follows the reference expression by expression, including the as-written ``view(-1, end-start)`` of the
+hop-major score vector for 'ori_ref' and 'jk' (SURVEY.md section 9 item 10).
+"""
+from __future__ import annotations
+
+import torch
+import torch.nn.functional as F
+from torch import nn
+from torch.nn import Linear, ModuleList, Parameter
+
+from ..base_op import MessageOp
+from ..utils import one_dim_weighted_add, two_dim_weighted_add
+
+
+class LearnableWeightedMessageOp(MessageOp):
+    """Per-node (or global) learnable hop weights.
+
+    'simple' / 'simple_allow_neg'  extra argument prop_steps        -> prop_steps+1 scalars
+    'gate'                         extra argument feat_dim          -> Linear(feat_dim, 1) per hop row
+    'ori_ref'                      extra argument feat_dim          -> Linear(2*feat_dim, 1) on [hop0 | hop_k]
+    'jk'                           extra arguments prop_steps, feat_dim -> Linear((prop_steps+2)*feat_dim, 1)
+    """
+
+    def __init__(self, start, end, combination_type, *args):
+        super(LearnableWeightedMessageOp, self).__init__(start, end)
+        self._aggr_type = "learnable_weighted"
+
+        if combination_type not in ["simple", "simple_allow_neg", "gate", "ori_ref", "jk"]:
+            raise ValueError(
+                "Invalid weighted combination type! Type must be 'simple', 'simple_allow_neg', 'gate', 'ori_ref' or 'jk'.")
+        self._combination_type = combination_type
+
+        expected = 2 if combination_type == "jk" else 1
+        if len(args) != expected:
+            raise ValueError(f"Invalid parameter numbers for the {combination_type} learnable weighted aggregator!")
+        if combination_type in ("simple", "simple_allow_neg"):
+            seed = torch.FloatTensor(1, args[0] + 1)  # xavier needs a 2-d tensor
+            nn.init.xavier_normal_(seed)
+            self._learnable_weight = Parameter(seed.view(-1))
+        elif combination_type == "gate":
+            self._learnable_weight = Linear(args[0], 1)
+        elif combination_type == "ori_ref":
+            self._learnable_weight = Linear(2 * args[0], 1)
+        else:
+            prop_steps, feat_dim = args
+            self._learnable_weight = Linear(feat_dim + (prop_steps + 1) * feat_dim, 1)
+
+    def hop_weights(self, feat_list):
+        kind, s, e = self._combination_type, self._start, self._end
+        if kind == "simple":
+            return F.softmax(torch.sigmoid(self._learnable_weight[s:e]), dim=0)
+        if kind == "simple_allow_neg":
+            return self._learnable_weight[s:e]
+        stacked = torch.vstack(feat_list[s:e])  # [(e-s)*B, d], hop-major
+        if kind == "gate":
+            score = self._learnable_weight(stacked).view(e - s, -1).T
+        else:
+            ref = feat_list[0] if kind == "ori_ref" else torch.hstack(feat_list)
+            score = self._learnable_weight(torch.hstack((ref.repeat(e - s, 1), stacked))).view(-1, e - s)
+        return F.softmax(torch.sigmoid(score), dim=1)
+
+    def _combine(self, feat_list):
+        weights = self.hop_weights(feat_list)
+        sel = feat_list[self._start:self._end]
+        if weights.dim() == 1:
+            return one_dim_weighted_add(sel, weight_list=weights)
+        return two_dim_weighted_add(sel, weight_list=weights)
+
+
+class IterateLearnableWeightedMessageOp(MessageOp):
+    """Recursive gated combination (reference iterate_learnable_weighted_message_op.py:8-51)."""
+
+    def __init__(self, start, end, combination_type, *args):
+        super(IterateLearnableWeightedMessageOp, self).__init__(start, end)
+        self._aggr_type = "iterate_learnable_weighted"
+        if combination_type not in ["recursive"]:
+            raise ValueError("Invalid weighted combination type! Type must be 'recursive'.")
+        self._combination_type = combination_type
+        if len(args) != 1:
+            raise ValueError("Invalid parameter numbers for the recursive iterate weighted aggregator!")
+        self._learnable_weight = Linear(2 * args[0], 1)
+
+    def _combine(self, feat_list):
+        s, e = self._start, self._end
+        combined = feat_list[s]
+        scores = None
+        for i in range(s, e):
+            gate = torch.sigmoid(self._learnable_weight(torch.hstack((feat_list[i], combined))))
+            scores = gate if scores is None else torch.hstack((scores, gate))
+            scores = F.softmax(scores, dim=1)  # the reference re-normalises the running matrix every step (:37)
+            combined = feat_list[s] * scores[:, 0:1]
+            for j in range(1, i + 1):
+                combined = combined + feat_list[s + j] * scores[:, j:j + 1]
+        return combined
+
+
+class _Mlp(nn.Module):
+    """Dense head used per hop: Linear -> shared PReLU -> Dropout(0.5) ... -> Linear, xavier(relu gain) weights and
+    zero biases (the behaviour of the reference's MultiLayerPerceptron, sgl/models/simple_models.py:101-140, which is
+    outside the hot path and therefore only restated as far as this op needs it)."""
+
+    def __init__(self, feat_dim, hidden_dim, num_layers, output_dim, dropout=0.5):
+        super().__init__()
+        if num_layers < 2:
+            raise ValueError("MLP must have at least two layers!")
+        dims = [feat_dim] + [hidden_dim] * (num_layers - 1) + [output_dim]
+        self.fcs = ModuleList(Linear(a, b) for a, b in zip(dims[:-1], dims[1:]))
+        self.act = nn.PReLU()
+        self.dropout = nn.Dropout(dropout)
+        gain = nn.init.calculate_gain("relu")
+        for fc in self.fcs:
+            nn.init.xavier_uniform_(fc.weight, gain=gain)
+            nn.init.zeros_(fc.bias)
+
+    def forward(self, x):
+        for fc in self.fcs[:-1]:
+            x = self.dropout(self.act(fc(x)))
+        return self.fcs[-1](x)
+
+
+class ProjectedConcatMessageOp(MessageOp):
+    """Per-hop MLP projection then concatenation (reference projected_concat_message_op.py:9-28)."""
+
+    def __init__(self, start, end, feat_dim, hidden_dim, num_layers):
+        super(ProjectedConcatMessageOp, self).__init__(start, end)
+        self._aggr_type = "proj_concat"
+        self._learnable_weight = ModuleList(
+            _Mlp(feat_dim, hidden_dim, num_layers, hidden_dim) for _ in range(end - start))
+
+    def _combine(self, feat_list):
+        sel = feat_list[self._start:self._end]
+        parts = [self._learnable_weight[0](sel[0])]
+        parts += [F.relu(mlp(f)) for mlp, f in zip(list(self._learnable_weight)[1:], sel[1:])]
+        return torch.hstack(parts)

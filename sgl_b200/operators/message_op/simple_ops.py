@@ -1,0 +1,147 @@
+"""Non-learnable cross-hop combiners on the B200 (reference sgl/operators/message_op/{last,sum,mean,max,min,concat,
+simple_weighted}_message_op.py and over_smooth_distance_op.py).
+
+Inputs are the K+1 hop tensors.  CUDA tensors are combined in place on their device; CPU tensors (what the
+reference's preprocess hands over) are uploaded, combined by the kernel and the result is returned on the CPU,
+so callers see the reference's types.  There is no CPU implementation behind these classes.
+"""
+from __future__ import annotations
+
+import torch
+from torch import Tensor
+
+from .. import utils as _u
+from ... import _lib
+from ...runtime import aggregate, require_cuda
+from ..base_op import MessageOp
+
+
+def _run(op: int, feats, weights=None) -> Tensor:
+    require_cuda()
+    on_cpu = not feats[0].is_cuda
+    dev_feats, _ = _u._to_cuda(list(feats))
+    out = aggregate(op, dev_feats, weights)
+    return out.cpu() if on_cpu else out
+
+
+class LastMessageOp(MessageOp):
+    """Keeps the last hop only (reference last_message_op.py:4-10)."""
+
+    def __init__(self):
+        super(LastMessageOp, self).__init__()
+        self._aggr_type = "last"
+
+    def _combine(self, feat_list):
+        return feat_list[-1]
+
+
+class SumMessageOp(MessageOp):
+    """Left-to-right float32 sum of hops [start, end) (reference sum_message_op.py:4-10)."""
+
+    def __init__(self, start, end):
+        super(SumMessageOp, self).__init__(start, end)
+        self._aggr_type = "sum"
+
+    def _combine(self, feat_list):
+        return _run(_lib.AGG_SUM, feat_list[self._start:self._end])
+
+
+class MeanMessageOp(MessageOp):
+    """Sum of hops [start, end) divided once by end-start (reference mean_message_op.py:4-10)."""
+
+    def __init__(self, start, end):
+        super(MeanMessageOp, self).__init__(start, end)
+        self._aggr_type = "mean"
+
+    def _combine(self, feat_list):
+        sel = feat_list[self._start:self._end]
+        if len(sel) != self._end - self._start:
+            # the reference divides by end-start even when the slice is shorter; keep that by scaling afterwards
+            return _run(_lib.AGG_SUM, sel) / (self._end - self._start)
+        return _run(_lib.AGG_MEAN, sel)
+
+
+class MaxMessageOp(MessageOp):
+    """Element-wise maximum over hops [start, end) (reference max_message_op.py:6-12)."""
+
+    def __init__(self, start, end):
+        super(MaxMessageOp, self).__init__(start, end)
+        self._aggr_type = "max"
+
+    def _combine(self, feat_list):
+        return _run(_lib.AGG_MAX, feat_list[self._start:self._end])
+
+
+class MinMessageOp(MessageOp):
+    """Element-wise minimum over hops [start, end) (reference min_message_op.py:6-12)."""
+
+    def __init__(self, start, end):
+        super(MinMessageOp, self).__init__(start, end)
+        self._aggr_type = "min"
+
+    def _combine(self, feat_list):
+        return _run(_lib.AGG_MIN, feat_list[self._start:self._end])
+
+
+class ConcatMessageOp(MessageOp):
+    """[N, (end-start)*d] horizontal stack of hops [start, end) (reference concat_message_op.py:6-12)."""
+
+    def __init__(self, start, end):
+        super(ConcatMessageOp, self).__init__(start, end)
+        self._aggr_type = "concat"
+
+    def _combine(self, feat_list):
+        return _run(_lib.AGG_CONCAT, feat_list[self._start:self._end])
+
+
+class SimpleWeightedMessageOp(MessageOp):
+    """Fixed scalar hop weights (reference simple_weighted_message_op.py:8-56).
+
+    'alpha'        one extra argument alpha (float in [0, 1]): w_0 = alpha, w_k = (1 - alpha) * w_{k-1}
+    'hand_crafted' one extra argument: the weight list (list or tensor)
+    """
+
+    def __init__(self, start, end, combination_type, *args):
+        super(SimpleWeightedMessageOp, self).__init__(start, end)
+        self._aggr_type = "simple_weighted"
+
+        if combination_type not in ["alpha", "hand_crafted"]:
+            raise ValueError("Invalid weighted combination type! Type must be 'alpha' or 'hand_crafted'.")
+        self._combination_type = combination_type
+
+        if len(args) != 1:
+            raise ValueError("Invalid parameter numbers for the simple weighted aggregator!")
+        self._alpha, self._weight_list = None, None
+        if combination_type == "alpha":
+            self._alpha = args[0]
+            if not isinstance(self._alpha, float):
+                raise TypeError("The alpha must be a float!")
+            elif self._alpha > 1 or self._alpha < 0:
+                raise ValueError("The alpha must be a float in [0,1]!")
+        else:
+            self._weight_list = args[0]
+            if isinstance(self._weight_list, list):
+                self._weight_list = torch.FloatTensor(self._weight_list)
+            elif not isinstance(self._weight_list, (list, Tensor)):
+                raise TypeError("The input weight list must be a list or a tensor!")
+
+    def _combine(self, feat_list):
+        if self._combination_type == "alpha":
+            # geometric weights in python float64, rounded to float32 once (reference :42-47)
+            weights = [self._alpha]
+            for _ in range(len(feat_list) - 1):
+                weights.append((1 - self._alpha) * weights[-1])
+            self._weight_list = torch.FloatTensor(weights[self._start:self._end])
+        return _u.one_dim_weighted_add(feat_list[self._start:self._end], weight_list=self._weight_list)
+
+
+class OverSmoothDistanceWeightedOp(MessageOp):
+    """NAFS hop weights: softmax over hops of the cosine between a node's raw and smoothed features
+    (reference over_smooth_distance_op.py:6-33, whose python loop over N x (K+1) becomes one warp per node)."""
+
+    def __init__(self):
+        super(OverSmoothDistanceWeightedOp, self).__init__()
+        self._aggr_type = 'over_smooth_dis_weighted'
+
+    def _combine(self, feat_list):
+        return _run(_lib.AGG_OSD, feat_list)

@@ -1,0 +1,124 @@
+"""sgap.py -- the SGAP model glue around the hot path (mirror of the reference's sgl/models/base_model.py:8-66).
+
+Only the preprocess / postprocess / forward contract is restated; datasets, tasks and the model zoo stay the
+reference's.  SGC / SSGC / SIGN / GBP / GAMLP / NAFS are given as the few-line wirings they are in the reference
+(sgl/models/homo/*.py) so that the parity tests and the benchmark can drive the path the way SGL does.
+"""
+from __future__ import annotations
+
+import torch
+import torch.nn as nn
+import torch.nn.functional as F
+
+from .operators.graph_op import LaplacianGraphOp
+from .operators.message_op import (ConcatMessageOp, LastMessageOp, LearnableWeightedMessageOp, MeanMessageOp,
+                                   OverSmoothDistanceWeightedOp, SimpleWeightedMessageOp)
+from .operators.message_op.learnable_ops import _Mlp
+
+_LEARNABLE = ("proj_concat", "learnable_weighted", "iterate_learnable_weighted")
+
+
+class BaseSGAPModel(nn.Module):
+    """preprocess = propagate (+ non-learnable aggregate); forward = row gather (+ learnable aggregate) + head."""
+
+    def __init__(self, prop_steps, feat_dim, output_dim):
+        super(BaseSGAPModel, self).__init__()
+        self._prop_steps = prop_steps
+        self._feat_dim = feat_dim
+        self._output_dim = output_dim
+
+        self._pre_graph_op, self._pre_msg_op = None, None
+        self._post_graph_op, self._post_msg_op = None, None
+        self._base_model = None
+
+        self._processed_feat_list = None
+        self._processed_feature = None
+        self._pre_msg_learnable = False
+
+    def preprocess(self, adj, feature):
+        """reference base_model.py:23-36"""
+        if self._pre_graph_op is None:
+            self._pre_msg_learnable = False
+            self._processed_feature = feature
+            return
+        self._processed_feat_list = self._pre_graph_op.propagate(adj, feature)
+        self._pre_msg_learnable = self._pre_msg_op.aggr_type in _LEARNABLE
+        if not self._pre_msg_learnable:
+            self._processed_feature = self._pre_msg_op.aggregate(self._processed_feat_list)
+
+    def postprocess(self, adj, output):
+        """reference base_model.py:38-49"""
+        if self._post_graph_op is not None:
+            if self._post_msg_op.aggr_type in _LEARNABLE:
+                raise ValueError(
+                    "Learnable weighted message operator is not supported in the post-processing phase!")
+            output = F.softmax(output, dim=1).detach().cpu().numpy()
+            output = self._post_graph_op.propagate(adj, output)
+            output = self._post_msg_op.aggregate(output)
+        return output
+
+    def model_forward(self, idx, device):
+        return self.forward(idx, device)
+
+    def forward(self, idx, device):
+        """reference base_model.py:55-66.  With hop slabs resident on the GPU (GraphOp.output_device == 'cuda') the
+        row gather runs on the device and `.to(device)` is a no-op."""
+        if self._pre_msg_learnable is False:
+            processed_feature = self._processed_feature[idx].to(device)
+        else:
+            transferred = [feat[idx].to(device) for feat in self._processed_feat_list]
+            processed_feature = self._pre_msg_op.aggregate(transferred)
+        return self._base_model(processed_feature)
+
+
+class _Identity(nn.Module):
+    def forward(self, feature):
+        return feature
+
+
+class SGC(BaseSGAPModel):        # reference sgl/models/homo/sgc.py:8-13
+    def __init__(self, prop_steps, feat_dim, output_dim):
+        super().__init__(prop_steps, feat_dim, output_dim)
+        self._pre_graph_op = LaplacianGraphOp(prop_steps, r=0.5)
+        self._pre_msg_op = LastMessageOp()
+        self._base_model = nn.Linear(feat_dim, output_dim)
+
+
+class SSGC(BaseSGAPModel):       # reference sgl/models/homo/ssgc.py
+    def __init__(self, prop_steps, feat_dim, output_dim):
+        super().__init__(prop_steps, feat_dim, output_dim)
+        self._pre_graph_op = LaplacianGraphOp(prop_steps, r=0.5)
+        self._pre_msg_op = MeanMessageOp(start=0, end=prop_steps + 1)
+        self._base_model = nn.Linear(feat_dim, output_dim)
+
+
+class SIGN(BaseSGAPModel):       # reference sgl/models/homo/sign.py
+    def __init__(self, prop_steps, feat_dim, output_dim, hidden_dim, num_layers):
+        super().__init__(prop_steps, feat_dim, output_dim)
+        self._pre_graph_op = LaplacianGraphOp(prop_steps, r=0.5)
+        self._pre_msg_op = ConcatMessageOp(start=0, end=prop_steps + 1)
+        self._base_model = _Mlp((prop_steps + 1) * feat_dim, hidden_dim, num_layers, output_dim)
+
+
+class GBP(BaseSGAPModel):        # reference sgl/models/homo/gbp.py:8-13
+    def __init__(self, prop_steps, feat_dim, output_dim, hidden_dim, num_layers, r=0.5, alpha=0.85):
+        super().__init__(prop_steps, feat_dim, output_dim)
+        self._pre_graph_op = LaplacianGraphOp(prop_steps, r=r)
+        self._pre_msg_op = SimpleWeightedMessageOp(0, prop_steps + 1, "alpha", alpha)
+        self._base_model = _Mlp(feat_dim, hidden_dim, num_layers, output_dim)
+
+
+class GAMLP(BaseSGAPModel):      # reference sgl/models/homo/gamlp.py:8-13
+    def __init__(self, prop_steps, feat_dim, output_dim, hidden_dim, num_layers):
+        super().__init__(prop_steps, feat_dim, output_dim)
+        self._pre_graph_op = LaplacianGraphOp(prop_steps, r=0.5)
+        self._pre_msg_op = LearnableWeightedMessageOp(0, prop_steps + 1, "jk", prop_steps, feat_dim)
+        self._base_model = _Mlp(feat_dim, hidden_dim, num_layers, output_dim)
+
+
+class NAFS(BaseSGAPModel):       # reference sgl/models/homo/nafs.py:8-13
+    def __init__(self, prop_steps, feat_dim, output_dim):
+        super().__init__(prop_steps, feat_dim, output_dim)
+        self._pre_graph_op = LaplacianGraphOp(prop_steps, r=0.5)
+        self._pre_msg_op = OverSmoothDistanceWeightedOp()
+        self._base_model = _Identity()

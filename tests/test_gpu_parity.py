@@ -1,0 +1,345 @@
+"""GPU parity tests (-m gpu): the CUDA path, called through the C ABI, against the oracle and the golden vectors.
+
+Bars: CSR structure and EXACT-mode hops bit-exact against the reference goldens / the oracle's fma chain;
+FAST-mode hops within 1e-5 (Frobenius-relative and max-abs relative to max|ref|, per hop: BASELINE.md section 4);
+sum/mean/max/min/concat/weighted combiners bit-exact; NAFS weights within 2e-6.
+Nothing here reads /root/reference.
+"""
+import ctypes
+import os
+
+import numpy as np
+import pytest
+import scipy.sparse as sp
+import torch
+
+from conftest import GRAPH_TAGS, golden_graph_files, load_graph
+from oracle import sgap_oracle as O
+
+pytestmark = pytest.mark.gpu
+
+if torch.cuda.is_available():
+    from sgl_b200 import _lib
+    from sgl_b200.operators.graph_op import LaplacianGraphOp, PprGraphOp
+    from sgl_b200.operators.message_op import (ConcatMessageOp, LastMessageOp, MaxMessageOp, MeanMessageOp,
+                                               MinMessageOp, OverSmoothDistanceWeightedOp, SimpleWeightedMessageOp,
+                                               SumMessageOp)
+    from sgl_b200.operators.utils import csr_sparse_dense_matmul, cuda_csr_sparse_dense_matmul
+    from sgl_b200.runtime import CsrOperator, aggregate, gather_rows
+
+
+def rel_errors(got, ref):
+    got = np.asarray(got, dtype=np.float64)
+    ref = np.asarray(ref, dtype=np.float64)
+    fro = np.linalg.norm(got - ref) / max(np.linalg.norm(ref), 1e-300)
+    mx = np.abs(got - ref).max() / max(np.abs(ref).max(), 1e-300) if ref.size else 0.0
+    return fro, mx
+
+
+def assert_close_1e5(got, ref):
+    fro, mx = rel_errors(got, ref)
+    assert fro <= 1e-5 and mx <= 1e-5, (fro, mx)
+
+
+def _scipy_adj(adj):
+    return sp.csr_matrix((adj.data, adj.indices, adj.indptr), shape=adj.shape)
+
+
+def random_graph(rng, n, m, skew=1.3, weights=False, undirected=True):
+    rows = rng.integers(0, n, m)
+    cols = (rng.zipf(skew, m) - 1) % n
+    if undirected:
+        rows, cols = np.concatenate([rows, cols]), np.concatenate([cols, rows])
+    vals = rng.uniform(0.25, 2.0, rows.size).astype(np.float32) if weights else np.ones(rows.size, dtype=np.float32)
+    return sp.csr_matrix((vals, (rows, cols)), shape=(n, n))
+
+
+# --------------------------------------------------------------------------------------------------------------
+# golden vectors from the unmodified reference
+# --------------------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("path", golden_graph_files(), ids=lambda p: os.path.basename(p)[6:-4])
+@pytest.mark.parametrize("tag,kind,r,alpha", GRAPH_TAGS)
+def test_golden_propagate(path, tag, kind, r, alpha):
+    z, adj = load_graph(path)
+    K = z[tag + "_hops_fma"].shape[0] - 1
+    op = LaplacianGraphOp(K, r=r) if kind == "lap" else PprGraphOp(K, r=r, alpha=alpha)
+    op.mode = "exact"
+    hops = op.propagate(_scipy_adj(adj), z["x"].copy())
+    assert len(hops) == K + 1 and all(isinstance(h, torch.Tensor) and h.dtype == torch.float32 and not h.is_cuda
+                                      for h in hops)
+    got = np.stack([h.numpy() for h in hops])
+    assert np.array_equal(got, z[tag + "_hops_fma"])                      # == shipped libmatmul.so, bit for bit
+    a = op._adj
+    assert np.array_equal(a.indptr, z[tag + "_norm_indptr"]) and np.array_equal(a.indices, z[tag + "_norm_indices"])
+    op.mode = "fast"
+    got = np.stack([h.numpy() for h in op.propagate(_scipy_adj(adj), z["x"].copy())])
+    for k in range(K + 1):
+        assert_close_1e5(got[k], z[tag + "_hops_fma"][k])
+        if tag + "_hops_f64" in z:
+            assert_close_1e5(got[k], z[tag + "_hops_f64"][k])             # north_star: scipy CPU path
+            assert_close_1e5(got[k], z[tag + "_hops_scipy32"][k])
+
+
+@pytest.mark.parametrize("path", golden_graph_files(), ids=lambda p: os.path.basename(p)[6:-4])
+def test_golden_wrapper_and_first_hop_aliases_input(path):
+    z, adj = load_graph(path)
+    op = LaplacianGraphOp(1, r=0.5)
+    x = z["x"].copy()
+    hops = op.propagate(_scipy_adj(adj), x)
+    assert hops[0].data_ptr() == torch.from_numpy(x).data_ptr()          # element 0 shares memory
+    assert np.array_equal(csr_sparse_dense_matmul(op._adj, x), z["wrapper_hop"])
+    assert_close_1e5(cuda_csr_sparse_dense_matmul(op._adj, x), z["wrapper_hop"])
+
+
+def test_golden_combiners(message_golden):
+    g = message_golden
+    hops = [torch.from_numpy(h) for h in g["hops"]]
+    dev = [h.cuda() for h in hops]
+    assert torch.equal(LastMessageOp().aggregate(hops), hops[-1])
+    for (s, e) in [(0, 5), (1, 4)]:
+        t = f"_{s}_{e}"
+        for feats in (hops, dev):     # CPU tensors in -> CPU out; CUDA in -> CUDA out
+            def run(op):
+                out = op.aggregate(feats)
+                assert out.is_cuda == feats[0].is_cuda
+                return out.cpu().numpy()
+            assert np.array_equal(run(SumMessageOp(s, e)), g["sum" + t])
+            assert np.array_equal(run(MeanMessageOp(s, e)), g["mean" + t])
+            assert np.array_equal(run(MaxMessageOp(s, e)), g["max" + t])
+            assert np.array_equal(run(MinMessageOp(s, e)), g["min" + t])
+            assert np.array_equal(run(ConcatMessageOp(s, e)), g["concat" + t])
+            assert np.array_equal(run(SimpleWeightedMessageOp(s, e, "alpha", 0.85)), g["alpha0.85" + t])
+            assert np.array_equal(run(SimpleWeightedMessageOp(s, e, "alpha", 0.1)), g["alpha0.1" + t])
+    out = SimpleWeightedMessageOp(0, 5, "hand_crafted", [float(v) for v in g["hand_weights"]]).aggregate(hops)
+    assert np.array_equal(out.numpy(), g["hand_0_5"])
+    osd = OverSmoothDistanceWeightedOp().aggregate(hops).numpy()
+    np.testing.assert_allclose(osd, g["osd"], rtol=2e-6, atol=2e-6)
+
+
+# --------------------------------------------------------------------------------------------------------------
+# oracle on seeded random inputs: every kernel shape, ragged rows, cut rows
+# --------------------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("d", [1, 3, 8, 16, 47, 64, 100, 128, 200, 256, 500, 1030])
+def test_feature_widths_exact_and_fast(d):
+    rng = np.random.default_rng(d)
+    n = 700
+    adj = random_graph(rng, n, 5000, weights=True)
+    a = O.laplacian_adj(adj, 0.5)
+    x = rng.standard_normal((n, d)).astype(np.float32)
+    ref = O.spmm_hop(a, x, "fma")
+    op = CsrOperator(a.indptr, a.indices, a.data.astype(np.float32), a.shape)
+    xd = torch.from_numpy(x).cuda()
+    assert np.array_equal(op.spmm(xd, mode="exact").cpu().numpy(), ref)
+    assert_close_1e5(op.spmm(xd, mode="fast").cpu().numpy(), ref)
+    op.close()
+
+
+@pytest.mark.parametrize("tile_items,split", [(32, 1), (32, 40), (128, 0), (512, 16)])
+def test_cut_rows_are_folded_deterministically(tile_items, split):
+    """tiny tiles + tiny split threshold force most rows across several warps: exercises the carry workspace."""
+    rng = np.random.default_rng(tile_items + split)
+    n, d = 400, 128
+    adj = random_graph(rng, n, 30000, skew=1.15)           # a few rows with thousands of entries
+    a = O.laplacian_adj(adj, 0.5)
+    x = rng.standard_normal((n, d)).astype(np.float32)
+    ref = O.spmm_hop(a, x, "fma")
+    op = CsrOperator(a.indptr, a.indices, a.data.astype(np.float32), a.shape, tile_items=tile_items,
+                     split_threshold=split)
+    info = op.info()
+    if split in (1, 16, 40):
+        assert info["carry_runs"] > 0
+    xd = torch.from_numpy(x).cuda()
+    y1 = op.spmm(xd, mode="fast").cpu().numpy()
+    y2 = op.spmm(xd, mode="fast").cpu().numpy()
+    assert np.array_equal(y1, y2)                           # run-to-run deterministic (no atomics)
+    assert_close_1e5(y1, ref)
+    assert np.array_equal(op.spmm(xd, mode="exact").cpu().numpy(), ref)
+    op.close()
+
+
+def test_empty_rows_empty_matrix_and_rectangular():
+    rng = np.random.default_rng(5)
+    # rows 0, 3 and the last 70 rows are empty; rectangular 200 x 90 operator (a row partition)
+    n_rows, n_cols, d = 200, 90, 36
+    rows = rng.integers(1, 130, 900)
+    rows = rows[rows != 3]
+    cols = rng.integers(0, n_cols, rows.size)
+    m = sp.csr_matrix((rng.standard_normal(rows.size).astype(np.float32), (rows, cols)), shape=(n_rows, n_cols))
+    m.sum_duplicates()
+    a = O.Csr(m.indptr, m.indices, m.data, m.shape)
+    x = rng.standard_normal((n_cols, d)).astype(np.float32)
+    ref = np.zeros((n_rows, d), dtype=np.float32)
+    O._lib().oracle_spmm_f32_fma_i64(ref, a.data.astype(np.float32), a.indices, a.indptr, x, n_rows, d)
+    op = CsrOperator(a.indptr, a.indices, a.data, a.shape, tile_items=32)
+    for mode in ("exact", "fast"):
+        y = op.spmm(torch.from_numpy(x).cuda(), mode=mode).cpu().numpy()
+        assert np.array_equal(y, ref) if mode == "exact" else np.allclose(y, ref, rtol=1e-5, atol=1e-6)
+        assert not y[0].any() and not y[3].any() and not y[130:].any()
+    op.close()
+    # nnz == 0 and n == 0
+    z = CsrOperator(np.zeros(6, dtype=np.int64), np.zeros(0, dtype=np.int32), np.zeros(0, dtype=np.float32), (5, 5))
+    assert not z.spmm(torch.ones(5, 4, device="cuda")).cpu().numpy().any()
+    z.close()
+    e = CsrOperator(np.zeros(1, dtype=np.int64), np.zeros(0, dtype=np.int32), np.zeros(0, dtype=np.float32), (0, 0))
+    assert e.spmm(torch.ones(0, 4, device="cuda")).shape == (0, 4)
+    e.close()
+
+
+def test_int32_indptr_device_inputs_and_strided_output():
+    rng = np.random.default_rng(9)
+    n, d, K = 300, 64, 3
+    adj = random_graph(rng, n, 2500)
+    a = O.laplacian_adj(adj, 0.5)
+    x = rng.standard_normal((n, d)).astype(np.float32)
+    ref = O.propagate(a, x, K, "fma")
+    op = CsrOperator(torch.from_numpy(a.indptr.astype(np.int32)).cuda(), torch.from_numpy(a.indices).cuda(),
+                     torch.from_numpy(a.data.astype(np.float32)).cuda(), a.shape)
+    hops = op.propagate(torch.from_numpy(x).cuda(), K, mode="exact", concat=True)
+    # the K+1 slabs are column blocks of one [n, (K+1) d] buffer == ConcatMessageOp(0, K+1) of the hop list
+    base = hops[0]
+    assert all(h.stride(0) == (K + 1) * d for h in hops)
+    for k in range(K + 1):
+        assert np.array_equal(hops[k].cpu().numpy(), ref[k])
+    whole = torch.as_strided(base, (n, (K + 1) * d), ((K + 1) * d, 1)).cpu().numpy()
+    assert np.array_equal(whole, O.combine_concat(ref, 0, K + 1))
+    op.close()
+
+
+def test_accumulate_matches_reference_answer_semantics():
+    """matmul.c:36-37 accumulates into the caller's buffer: each chain starts from the value already there."""
+    rng = np.random.default_rng(11)
+    n, d = 256, 100
+    adj = random_graph(rng, n, 3000, weights=True)
+    a = O.laplacian_adj(adj, 0.3)
+    x = rng.standard_normal((n, d)).astype(np.float32)
+    y0 = rng.standard_normal((n, d)).astype(np.float32)
+    ref = y0.copy()
+    O._lib().oracle_spmm_f32_fma_i64(ref, a.data.astype(np.float32), a.indices, a.indptr, x, n, d)
+    op = CsrOperator(a.indptr, a.indices, a.data.astype(np.float32), a.shape)
+    y = torch.from_numpy(y0.copy()).cuda()
+    op.spmm(torch.from_numpy(x).cuda(), out=y, accumulate=True)
+    assert np.array_equal(y.cpu().numpy(), ref)
+    op.close()
+
+
+def test_legacy_abi_symbols_bit_exact():
+    """The reference's two C entry points, same signatures, host pointers (matmul.h:5, cudamatmul.c:28)."""
+    rng = np.random.default_rng(13)
+    n, d = 500, 96
+    adj = random_graph(rng, n, 6000, weights=True)
+    a = O.laplacian_adj(adj, 0.5)
+    data = a.data.astype(np.float32)
+    indptr32 = a.indptr.astype(np.int32)
+    x = rng.standard_normal((n, d)).astype(np.float32)
+    ref = O.spmm_hop(a, x, "fma")
+    lib = _lib.load()
+    ans = np.zeros(n * d, dtype=np.float32)
+    lib.FloatCSRMulDenseOMP(ans.ctypes.data, data.ctypes.data, a.indices.ctypes.data, indptr32.ctypes.data,
+                            x.reshape(-1).ctypes.data, n, d)
+    assert np.array_equal(ans.reshape(n, d), ref)
+    ans2 = np.full(n * d, 7.0, dtype=np.float32)          # the cuSPARSE-style entry overwrites (beta = 0)
+    rc = lib.FloatCSRMulDense(ans2.ctypes.data, int(a.nnz), data.ctypes.data, a.indices.ctypes.data,
+                              indptr32.ctypes.data, x.reshape(-1).ctypes.data, n, d)
+    assert rc == 0 and np.array_equal(ans2.reshape(n, d), ref)
+    ref_lib = O.load_reference_kernel()
+    if ref_lib is not None:                                  # the reference's own kernel, compiled from its source
+        assert np.array_equal(O.reference_kernel_hop(ref_lib, a, x), ans.reshape(n, d))
+
+
+def test_propagate_host_keep_last_and_torch_feature():
+    rng = np.random.default_rng(17)
+    n, d, K = 1200, 128, 5
+    adj = random_graph(rng, n, 9000)
+    a = O.laplacian_adj(adj, 0.5)
+    x = rng.standard_normal((n, d)).astype(np.float32)
+    ref = O.propagate(a, x, K, "fma")
+    op = CsrOperator(a.indptr, a.indices, a.data.astype(np.float32), a.shape)
+    outs = op.propagate_host(x, K, mode="exact", keep="last")
+    assert outs[:-1] == [None] * (K - 1) and np.array_equal(outs[-1].numpy(), ref[K])
+    outs = op.propagate_host(torch.from_numpy(x), K, mode="exact", keep="all")
+    for k in range(1, K + 1):
+        assert np.array_equal(outs[k - 1].numpy(), ref[k])
+    op.close()
+    # dataset.x is a torch.FloatTensor in the reference's own callers: accepted
+    g = LaplacianGraphOp(K)
+    g.mode = "exact"
+    hops = g.propagate(adj, torch.from_numpy(x))
+    assert np.array_equal(hops[K].numpy(), ref[K])
+
+
+def test_cuda_resident_outputs_and_gather():
+    rng = np.random.default_rng(19)
+    n, d, K = 900, 100, 3
+    adj = random_graph(rng, n, 7000)
+    x = rng.standard_normal((n, d)).astype(np.float32)
+    g = LaplacianGraphOp(K)
+    g.mode = "exact"
+    g.output_device = "cuda"
+    hops = g.propagate(adj, x)
+    ref = O.propagate(O.laplacian_adj(adj, 0.5), x, K, "fma")
+    assert all(h.is_cuda for h in hops)
+    for k in range(K + 1):
+        assert np.array_equal(hops[k].cpu().numpy(), ref[k])
+    idx = torch.from_numpy(rng.integers(0, n, 257))
+    outs = gather_rows(hops, idx)
+    for k in range(K + 1):
+        assert np.array_equal(outs[k].cpu().numpy(), ref[k][idx.numpy()])
+
+
+def test_nafs_weights_against_oracle_larger():
+    rng = np.random.default_rng(23)
+    n, d, K = 3000, 128, 6
+    adj = random_graph(rng, n, 20000)
+    x = rng.standard_normal((n, d)).astype(np.float32)
+    ref = O.propagate(O.laplacian_adj(adj, 0.5), x, K, "fma")
+    out = aggregate(_lib.AGG_OSD, [torch.from_numpy(r).cuda() for r in ref]).cpu().numpy()
+    np.testing.assert_allclose(out, O.combine_osd(ref), rtol=3e-6, atol=3e-6)
+
+
+# --------------------------------------------------------------------------------------------------------------
+# BASELINE.json sizes: size-independent properties (the oracle on a row sample, linearity, constant vectors)
+# --------------------------------------------------------------------------------------------------------------
+def _rmat_like(rng, n, m):
+    rows = (rng.zipf(1.25, m) - 1) % n
+    cols = rng.integers(0, n, m)
+    r2, c2 = np.concatenate([rows, cols]), np.concatenate([cols, rows])
+    return sp.csr_matrix((np.ones(r2.size, dtype=np.float32), (r2, c2)), shape=(n, n))
+
+
+def test_arxiv_shape_properties():
+    """configs[1] shape: N=169,343, ~2.3M undirected entries, d=128, K=5."""
+    rng = np.random.default_rng(29)
+    n, d, K = 169_343, 128, 5
+    adj = _rmat_like(rng, n, 1_166_243)
+    op = LaplacianGraphOp(K, r=0.5)
+    x = rng.standard_normal((n, d)).astype(np.float32)
+    hops = op.propagate(adj, x)
+    a = op._adj
+    a32 = a.astype(np.float32)
+    # (1) oracle on a row sample of every hop: y_k[i] from y_{k-1} (one-hop check isolates the kernel)
+    sample = rng.choice(n, 4000, replace=False)
+    sub = a32[sample]
+    sub_o = O.Csr(sub.indptr, sub.indices, sub.data, sub.shape)
+    for k in range(1, K + 1):
+        ref = np.zeros((sample.size, d), dtype=np.float32)
+        O._lib().oracle_spmm_f32_fma_i64(ref, sub_o.data, sub_o.indices, sub_o.indptr, hops[k - 1].numpy(),
+                                         sample.size, d)
+        assert_close_1e5(hops[k].numpy()[sample], ref)
+    # (2) r = 0 normalisation is row-stochastic: constant vectors are fixed points of every hop
+    op0 = LaplacianGraphOp(3, r=0.0)
+    ones = np.ones((n, 4), dtype=np.float32)
+    for h in op0.propagate(adj, ones):
+        np.testing.assert_allclose(h.numpy(), 1.0, rtol=0, atol=2e-6)
+    # (3) linearity: A(2x + y) == 2 Ax + Ay within fp32 rounding
+    csr = CsrOperator.from_scipy(a)
+    xd = torch.from_numpy(x).cuda()
+    yd = torch.from_numpy(rng.standard_normal((n, d)).astype(np.float32)).cuda()
+    lhs = csr.spmm(2 * xd + yd)
+    rhs = 2 * csr.spmm(xd) + csr.spmm(yd)
+    assert_close_1e5(lhs.cpu().numpy(), rhs.cpu().numpy())
+    # (4) fast and exact schedules agree to tolerance on the full-size graph, exact is reproducible
+    e1 = csr.spmm(xd, mode="exact")
+    e2 = csr.spmm(xd, mode="exact")
+    assert torch.equal(e1, e2)
+    assert_close_1e5(csr.spmm(xd, mode="fast").cpu().numpy(), e1.cpu().numpy())
+    csr.close()

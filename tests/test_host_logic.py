@@ -1,0 +1,144 @@
+"""CPU tests of the host-side mirror of sgl.operators: normalisation parity with the reference goldens, argument
+checking and error behaviour, and the loud failure when no GPU is present."""
+import os
+
+import numpy as np
+import pytest
+import scipy.sparse as sp
+import torch
+
+from conftest import GRAPH_TAGS, golden_graph_files, load_graph
+from sgl_b200 import SglB200Error
+from sgl_b200.operators.graph_op import LaplacianGraphOp, PprGraphOp
+from sgl_b200.operators.message_op import (ConcatMessageOp, LastMessageOp, LearnableWeightedMessageOp, MaxMessageOp,
+                                           MeanMessageOp, OverSmoothDistanceWeightedOp, SimpleWeightedMessageOp,
+                                           SumMessageOp, IterateLearnableWeightedMessageOp)
+from sgl_b200.operators.utils import adj_to_symmetric_norm, one_dim_weighted_add, two_dim_weighted_add
+
+HAS_GPU = torch.cuda.is_available()
+
+
+def _scipy_adj(adj):
+    return sp.csr_matrix((adj.data, adj.indices, adj.indptr), shape=adj.shape)
+
+
+@pytest.mark.parametrize("path", golden_graph_files(), ids=lambda p: os.path.basename(p)[6:-4])
+@pytest.mark.parametrize("tag,kind,r,alpha", GRAPH_TAGS)
+def test_construct_adj_matches_reference(path, tag, kind, r, alpha):
+    z, adj = load_graph(path)
+    op = LaplacianGraphOp(3, r=r) if kind == "lap" else PprGraphOp(3, r=r, alpha=alpha)
+    a = op._construct_adj(_scipy_adj(adj)).tocsr()
+    assert np.array_equal(a.indptr.astype(np.int64), z[tag + "_norm_indptr"])
+    assert np.array_equal(a.indices.astype(np.int32), z[tag + "_norm_indices"])
+    assert a.data.dtype == np.float64
+    assert np.array_equal(a.data, z[tag + "_norm_data"])
+    # COO input is accepted like in the reference
+    b = op._construct_adj(_scipy_adj(adj).tocoo()).tocsr()
+    assert np.array_equal(b.data, a.data)
+
+
+def test_symmetric_norm_formula_directed():
+    # edges 0->1, 0->2: A^[1,0] = A^[2,0] = 1/sqrt(3), A^[0,0] = 1/3
+    a = sp.csr_matrix((np.ones(2, dtype=np.float32), ([0, 0], [1, 2])), shape=(3, 3))
+    n = adj_to_symmetric_norm(a, 0.5).toarray()
+    assert n[1, 0] == pytest.approx(3 ** -0.5) and n[2, 0] == pytest.approx(3 ** -0.5)
+    assert n[0, 0] == pytest.approx(1 / 3) and n[1, 1] == 1.0 and n[0, 1] == 0.0
+
+
+def test_propagate_argument_errors():
+    a = sp.csr_matrix(np.eye(3, dtype=np.float32))
+    x = np.ones((3, 2), dtype=np.float32)
+    with pytest.raises(TypeError):
+        LaplacianGraphOp(1).propagate(a.todense(), x)            # not sparse: _construct_adj rejects
+    with pytest.raises(TypeError):
+        LaplacianGraphOp(1).propagate(a.tocoo(), x)              # COO passes _construct_adj, fails the CSR check
+    with pytest.raises(TypeError):
+        LaplacianGraphOp(1).propagate(a, [[1.0, 2.0]] * 3)       # feature must be an ndarray (or tensor)
+    with pytest.raises(ValueError):
+        LaplacianGraphOp(1).propagate(a, np.ones((4, 2), dtype=np.float32))
+    if not HAS_GPU:
+        with pytest.raises(SglB200Error):
+            LaplacianGraphOp(1).propagate(a, x)                  # no silent CPU path
+        with pytest.raises(TypeError):
+            LaplacianGraphOp(1).propagate(a, x.astype(np.float64))
+
+
+def test_message_op_validation_and_types():
+    assert LastMessageOp().aggr_type == "last"
+    assert SumMessageOp(0, 2).aggr_type == "sum" and MeanMessageOp(0, 2).aggr_type == "mean"
+    assert MaxMessageOp(0, 2).aggr_type == "max" and ConcatMessageOp(0, 2).aggr_type == "concat"
+    assert OverSmoothDistanceWeightedOp().aggr_type == "over_smooth_dis_weighted"
+    assert LearnableWeightedMessageOp(0, 3, "gate", 8).aggr_type == "learnable_weighted"
+    assert IterateLearnableWeightedMessageOp(0, 3, "recursive", 8).aggr_type == "iterate_learnable_weighted"
+    with pytest.raises(ValueError):
+        SimpleWeightedMessageOp(0, 2, "nope", 0.5)
+    with pytest.raises(TypeError):
+        SimpleWeightedMessageOp(0, 2, "alpha", 1)
+    with pytest.raises(ValueError):
+        SimpleWeightedMessageOp(0, 2, "alpha", 1.5)
+    with pytest.raises(ValueError):
+        LearnableWeightedMessageOp(0, 2, "jk", 3)
+    with pytest.raises(TypeError):
+        SumMessageOp(0, 2).aggregate([np.zeros((2, 2))])
+    with pytest.raises(TypeError):
+        SumMessageOp(0, 2).aggregate(torch.zeros(2, 2))
+    f = [torch.ones(4, 3), torch.full((4, 3), 2.0)]
+    assert torch.equal(LastMessageOp().aggregate(f), f[-1])
+    if not HAS_GPU:
+        with pytest.raises(SglB200Error):
+            SumMessageOp(0, 2).aggregate(f)
+
+
+def test_weighted_add_helpers_errors_and_autograd():
+    f = [torch.randn(5, 3), torch.randn(5, 3)]
+    with pytest.raises(TypeError):
+        one_dim_weighted_add(f, [0.5, 0.5])
+    with pytest.raises(ValueError):
+        one_dim_weighted_add(f, torch.ones(3))
+    with pytest.raises(ValueError):
+        two_dim_weighted_add(f, torch.ones(5, 3))
+    w = torch.tensor([0.25, 0.75], requires_grad=True)
+    out = one_dim_weighted_add(f, w)          # autograd branch: plain tensor algebra, usable on CPU
+    out.sum().backward()
+    assert torch.allclose(w.grad, torch.stack([f[0].sum(), f[1].sum()]))
+    w2 = torch.rand(5, 2)
+    ref = torch.bmm(torch.stack(f, dim=2), w2.unsqueeze(2)).squeeze(2)
+    assert torch.allclose(two_dim_weighted_add(f, w2), ref, atol=1e-6)
+
+
+@pytest.mark.parametrize("kind", ["simple", "simple_allow_neg", "gate", "ori_ref", "jk"])
+@pytest.mark.parametrize("se", [(0, 5), (1, 4)])
+def test_learnable_forward_matches_reference(message_golden, kind, se):
+    g = message_golden
+    s, e = se
+    K, d = 4, 16
+    batch = [torch.from_numpy(h[g["batch_idx"]]) for h in g["hops"]]
+    args = {"simple": (K,), "simple_allow_neg": (K,), "gate": (d,), "ori_ref": (d,), "jk": (K, d)}[kind]
+    op = LearnableWeightedMessageOp(s, e, kind, *args)
+    tag = f"lw_{kind}_{s}_{e}"
+    with torch.no_grad():
+        if kind in ("simple", "simple_allow_neg"):
+            op._learnable_weight.copy_(torch.from_numpy(g[tag + "_w"]))
+        else:
+            op._learnable_weight.weight.copy_(torch.from_numpy(g[tag + "_w"]))
+            op._learnable_weight.bias.copy_(torch.from_numpy(g[tag + "_b"]))
+    feats = [b.clone().requires_grad_(True) for b in batch]
+    out = op.aggregate(feats)
+    np.testing.assert_allclose(out.detach().numpy(), g[tag + "_out"], rtol=1e-5, atol=1e-6)
+    gout = torch.linspace(-1, 1, out.numel()).reshape(out.shape)
+    out.backward(gout)
+    gin = np.stack([f.grad.numpy() if f.grad is not None else np.zeros((len(g["batch_idx"]), d), np.float32)
+                    for f in feats])
+    np.testing.assert_allclose(gin, g[tag + "_gin"], rtol=1e-4, atol=1e-5)
+    gw = op._learnable_weight.grad if kind.startswith("simple") else op._learnable_weight.weight.grad
+    np.testing.assert_allclose(gw.numpy(), g[tag + "_gw"], rtol=1e-4, atol=1e-5)
+
+
+def test_iterate_learnable_matches_reference(message_golden):
+    g = message_golden
+    batch = [torch.from_numpy(h[g["batch_idx"]]) for h in g["hops"]]
+    op = IterateLearnableWeightedMessageOp(0, 5, "recursive", 16)
+    with torch.no_grad():
+        op._learnable_weight.weight.copy_(torch.from_numpy(g["iter_w"]))
+        op._learnable_weight.bias.copy_(torch.from_numpy(g["iter_b"]))
+    np.testing.assert_allclose(op.aggregate(batch).detach().numpy(), g["iter_out"], rtol=1e-5, atol=1e-6)
