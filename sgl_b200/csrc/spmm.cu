@@ -17,6 +17,7 @@
 //   * rows cut across warps (FAST schedule, rows longer than split_threshold) leave partial sums in a small
 //     workspace that a second kernel folds in tile order -- deterministic, no atomics.
 #include <limits.h>
+#include <stdlib.h>
 
 #include "common.cuh"
 
@@ -93,140 +94,141 @@ __device__ __forceinline__ float load_stream_f32(const float *p)
     return v;
 }
 
-template <int VEC, int VPL, int U, bool ACCUM>
-__global__ void __launch_bounds__(kWarpsPerBlock * 32) spmm_flat_kernel(const SpmmParams p)
+template <int VEC, int VPL, int U, bool ACCUM, int MINB>
+__global__ void __launch_bounds__(kWarpsPerBlock * 32, MINB) spmm_flat_kernel(const SpmmParams p)
 {
+    static_assert(32 % U == 0, "U must divide the batch of 32 non-zeros");
+    // (column id, value bits) of the current batch of 32 non-zeros, per warp, double buffered: one LDS.64 broadcast
+    // per non-zero hands every lane both the row to gather and its weight
+    __shared__ int2 s_pairs[kWarpsPerBlock][2][32];
     const int lane = threadIdx.x & 31;
     const int64_t t = (int64_t)blockIdx.x * kWarpsPerBlock + (threadIdx.x >> 5);
     if (t >= p.n_tiles) return;
+    int2 *pairs = &s_pairs[threadIdx.x >> 5][0][0];
 
-    int64_t row = p.tile_row[t];
-    const int64_t row_end = p.tile_row[t + 1];
+    int row = p.tile_row[t];
+    const int row_end = p.tile_row[t + 1];
     const int64_t j0 = p.tile_nnz[t];
     const int n_nnz = (int)(p.tile_nnz[t + 1] - j0);
+    const int n_rows = (int)p.n_rows;
 
-    // this lane's column slices of the output row
+    // this lane's column slices of the output row.  Slices beyond d are parked on a valid offset for the gathers
+    // (same sector as an active lane: no extra traffic, no predicate in the hot loop) and masked at the stores.
+    // Row addresses are ONE 32x32->64 multiply-add each: base pointer (kept in registers) + id * stride-in-bytes.
     const int col_block = blockIdx.y * (32 * VEC * VPL);
-    int cofs[VPL];
     bool act[VPL];
+    const char *xbase[VPL];
+    char *ybase[VPL];
 #pragma unroll
     for (int v = 0; v < VPL; ++v) {
-        cofs[v] = col_block + (v * 32 + lane) * VEC;
-        act[v] = cofs[v] < p.d;
+        const int cofs = col_block + (v * 32 + lane) * VEC;
+        act[v] = cofs < p.d;
+        xbase[v] = reinterpret_cast<const char *>(p.X) + (size_t)(act[v] ? cofs : col_block) * sizeof(float);
+        ybase[v] = reinterpret_cast<char *>(p.Y) + (size_t)cofs * sizeof(float);
+        asm volatile("" : "+l"(xbase[v]));  // materialise: keeps the compiler from re-adding the parameter every load
+        asm volatile("" : "+l"(ybase[v]));
     }
+    const uint32_t ldx_bytes = (uint32_t)p.ldx * (uint32_t)sizeof(float);  // strides < 2^30 elements (host check)
+    const uint32_t ldy_bytes = (uint32_t)p.ldy * (uint32_t)sizeof(float);
     float acc[VPL][VEC];
 
-    auto init_acc = [&](int64_t r) {
+    auto init_acc = [&](int r) {
 #pragma unroll
         for (int v = 0; v < VPL; ++v) {
 #pragma unroll
             for (int e = 0; e < VEC; ++e) acc[v][e] = 0.0f;
             if (ACCUM) {
-                if (act[v] && r < p.n_rows) load_plain<VEC>(acc[v], p.Y + r * p.ldy + cofs[v]);
+                if (act[v] && r < n_rows)
+                    load_plain<VEC>(acc[v], reinterpret_cast<const float *>(ybase[v] + (uint64_t)(uint32_t)r * ldy_bytes));
             }
         }
     };
 
-    // ends (relative to j0) of rows row_base .. row_base+31, one per lane
-    auto load_row_ends = [&](int64_t base) -> int {
-        const int64_t r = base + 1 + lane;
-        if (r > p.n_rows) return INT_MAX;
+    // ends (relative to j0) of rows row_base .. row_base+31, one per lane, refilled every 32 finished rows
+    auto load_row_ends = [&](int base) -> int {
+        const int r = base + 1 + lane;
+        if (r > n_rows) return INT_MAX;
         const int64_t rel = p.indptr[r] - j0;
         return rel > (int64_t)INT_MAX ? INT_MAX : (int)rel;
     };
-    int64_t row_base = row;
+    int row_base = row;
     int my_end = load_row_ends(row_base);
+    // next_end: tile-relative position at which the current row ends; INT_MAX once the tile owns no further row end
     int next_end = __shfl_sync(kFull, my_end, 0);
+    if (row >= row_end) next_end = INT_MAX;
 
     if (ACCUM) {
         // the chain of a row starts from the value already in Y only in the tile that holds the row start
-        const bool starts_here = row < p.n_rows && p.indptr[row] == j0;
-        init_acc(starts_here ? row : p.n_rows);
+        const bool starts_here = row < n_rows && p.indptr[row] == j0;
+        init_acc(starts_here ? row : n_rows);
     } else {
-        init_acc(p.n_rows);
+        init_acc(n_rows);
     }
 
     auto flush_row = [&]() {
-        float *yrow = p.Y + row * p.ldy;
 #pragma unroll
         for (int v = 0; v < VPL; ++v)
-            if (act[v]) store_slice<VEC>(yrow + cofs[v], acc[v]);
+            if (act[v]) store_slice<VEC>(reinterpret_cast<float *>(ybase[v] + (uint64_t)(uint32_t)row * ldy_bytes), acc[v]);
         ++row;
         if (row - row_base == 32) {
             row_base = row;
             my_end = load_row_ends(row_base);
         }
-        next_end = __shfl_sync(kFull, my_end, (int)(row - row_base));
+        const int e = __shfl_sync(kFull, my_end, row - row_base);
+        next_end = row < row_end ? e : INT_MAX;
         init_acc(row);  // every later row of the tile starts inside the tile
     };
 
     const int32_t *cols = p.indices + j0;
     const float *vals = p.vals + j0;
 
+    // (col, val) of the next 32 non-zeros are fetched one batch ahead of their use
+    int32_t col_next = 0;
+    float val_next = 0.0f;
+    if (lane < n_nnz) {
+        col_next = load_stream_i32(cols + lane);
+        val_next = load_stream_f32(vals + lane);
+    }
+#pragma unroll 1
     for (int base = 0; base < n_nnz; base += 32) {
-        const int n_here = min(32, n_nnz - base);
-        int32_t my_col = 0;
-        float my_val = 0.0f;
-        if (lane < n_here) {
-            my_col = load_stream_i32(cols + base + lane);
-            my_val = load_stream_f32(vals + base + lane);
+        // lanes past the end of the tile publish (column 0, weight 0): a valid row to gather, FMAs predicated off
+        int2 *batch = pairs + (base & 32);
+        batch[lane] = make_int2(col_next, __float_as_int(val_next));
+        __syncwarp();
+        col_next = 0;
+        val_next = 0.0f;
+        if (base + 32 + lane < n_nnz) {
+            col_next = load_stream_i32(cols + base + 32 + lane);
+            val_next = load_stream_f32(vals + base + 32 + lane);
         }
-        if (n_here == 32) {
+        const int n_here = min(32, n_nnz - base);
+#pragma unroll 1
+        for (int k = 0; k < n_here; k += U) {
+            // U gathered feature rows in flight before the first one is consumed
+            float x[U][VPL][VEC];
+            float w[U];
 #pragma unroll
-            for (int k = 0; k < 32; k += U) {
-                float x[U][VPL][VEC];
+            for (int u = 0; u < U; ++u) {
+                const int2 cv = batch[k + u];
+                w[u] = __int_as_float(cv.y);
 #pragma unroll
-                for (int u = 0; u < U; ++u) {
-                    const int32_t c = __shfl_sync(kFull, my_col, k + u);
-                    const float *xrow = p.X + (int64_t)c * p.ldx;
-#pragma unroll
-                    for (int v = 0; v < VPL; ++v) {
-                        if (act[v]) load_row_slice<VEC>(x[u][v], xrow + cofs[v]);
-                        else {
-#pragma unroll
-                            for (int e = 0; e < VEC; ++e) x[u][v][e] = 0.0f;
-                        }
-                    }
-                }
-#pragma unroll
-                for (int u = 0; u < U; ++u) {
-                    const int jj = base + k + u;
-                    while (jj == next_end && row < row_end) flush_row();
-                    const float w = __shfl_sync(kFull, my_val, k + u);
-#pragma unroll
-                    for (int v = 0; v < VPL; ++v)
-#pragma unroll
-                        for (int e = 0; e < VEC; ++e) acc[v][e] = fmaf(w, x[u][v][e], acc[v][e]);
-                }
+                for (int v = 0; v < VPL; ++v)
+                    load_row_slice<VEC>(x[u][v], reinterpret_cast<const float *>(xbase[v] + (uint64_t)(uint32_t)cv.x * ldx_bytes));
             }
-        } else {
-            for (int k = 0; k < n_here; k += U) {
-                float x[U][VPL][VEC];
+            const int pos = base + k;
+            const int valid = n_nnz - pos;   // >= U except in the padded tail of the last group
+            int left = next_end - pos;       // non-zeros of the current row still ahead, counted from the group start
 #pragma unroll
-                for (int u = 0; u < U; ++u) {
-                    const int32_t c = __shfl_sync(kFull, my_col, (k + u) & 31);
-                    const float *xrow = p.X + (int64_t)c * p.ldx;
-#pragma unroll
-                    for (int v = 0; v < VPL; ++v) {
-                        if (act[v] && k + u < n_here) load_row_slice<VEC>(x[u][v], xrow + cofs[v]);
-                        else {
-#pragma unroll
-                            for (int e = 0; e < VEC; ++e) x[u][v][e] = 0.0f;
-                        }
-                    }
+            for (int u = 0; u < U; ++u) {
+                while (u == left) {          // warp-uniform: the current row ends here (also retires empty rows)
+                    flush_row();
+                    left = next_end - pos;
                 }
+                const bool in_tile = u < valid;
 #pragma unroll
-                for (int u = 0; u < U; ++u) {
-                    const float w = __shfl_sync(kFull, my_val, (k + u) & 31);
-                    if (k + u < n_here) {
-                        const int jj = base + k + u;
-                        while (jj == next_end && row < row_end) flush_row();
+                for (int v = 0; v < VPL; ++v)
 #pragma unroll
-                        for (int v = 0; v < VPL; ++v)
-#pragma unroll
-                            for (int e = 0; e < VEC; ++e) acc[v][e] = fmaf(w, x[u][v][e], acc[v][e]);
-                    }
-                }
+                    for (int e = 0; e < VEC; ++e) acc[v][e] = in_tile ? fmaf(w[u], x[u][v][e], acc[v][e]) : acc[v][e];
             }
         }
     }
@@ -238,7 +240,7 @@ __global__ void __launch_bounds__(kWarpsPerBlock * 32) spmm_flat_kernel(const Sp
         float *wrow = p.carry_ws + (int64_t)slot * p.ws_ld;
 #pragma unroll
         for (int v = 0; v < VPL; ++v)
-            if (act[v]) store_slice<VEC>(wrow + cofs[v], acc[v]);
+            if (act[v]) store_slice<VEC>(wrow + col_block + (v * 32 + lane) * VEC, acc[v]);
     }
 }
 
@@ -258,7 +260,17 @@ __global__ void __launch_bounds__(kWarpsPerBlock * 32)
     for (int c = lane * VEC; c < d; c += 32 * VEC) {
         float sum[VEC];
         load_plain<VEC>(sum, ws + base * ws_ld + c);
-        for (int u = 1; u < len; ++u) {
+        int u = 1;
+        for (; u + 4 <= len; u += 4) {  // four partials in flight, added strictly in tile order
+            float part[4][VEC];
+#pragma unroll
+            for (int q = 0; q < 4; ++q) load_plain<VEC>(part[q], ws + (base + u + q) * ws_ld + c);
+#pragma unroll
+            for (int q = 0; q < 4; ++q)
+#pragma unroll
+                for (int e = 0; e < VEC; ++e) sum[e] += part[q][e];
+        }
+        for (; u < len; ++u) {
             float part[VEC];
             load_plain<VEC>(part, ws + (base + u) * ws_ld + c);
 #pragma unroll
@@ -272,12 +284,24 @@ __global__ void __launch_bounds__(kWarpsPerBlock * 32)
     }
 }
 
-template <int VEC, int VPL, int U>
+template <int VEC, int VPL, int U, int MINB>
 static cudaError_t launch_flat(const SpmmParams &p, bool accum, dim3 grid, cudaStream_t stream)
 {
-    if (accum) spmm_flat_kernel<VEC, VPL, U, true><<<grid, kWarpsPerBlock * 32, 0, stream>>>(p);
-    else spmm_flat_kernel<VEC, VPL, U, false><<<grid, kWarpsPerBlock * 32, 0, stream>>>(p);
+    if (accum) spmm_flat_kernel<VEC, VPL, U, true, (MINB > 3 ? 3 : MINB)><<<grid, kWarpsPerBlock * 32, 0, stream>>>(p);
+    else spmm_flat_kernel<VEC, VPL, U, false, MINB><<<grid, kWarpsPerBlock * 32, 0, stream>>>(p);
     return cudaGetLastError();
+}
+
+// tuning knob for experiments: SGLB200_SPMM_VARIANT selects (rows in flight per warp, resident CTAs per SM) of the
+// d = 128 kernel; unset = the measured best
+static int spmm_variant()
+{
+    static int v = -2;
+    if (v == -2) {
+        const char *e = getenv("SGLB200_SPMM_VARIANT");
+        v = e ? atoi(e) : -1;
+    }
+    return v;
 }
 
 static bool aligned(const void *p, size_t a) { return (reinterpret_cast<uintptr_t>(p) % a) == 0; }
@@ -315,6 +339,7 @@ int spmm_launch(sglb200_graph *g, const float *X, int64_t ldx, float *Y, int64_t
     if (g->n_rows == 0 || d == 0) return SGLB200_OK;
     SGL_REQUIRE(X != nullptr && Y != nullptr, "spmm: X or Y is NULL");
     SGL_REQUIRE(ldx >= d && ldy >= d, "spmm: row stride smaller than the feature width");
+    SGL_REQUIRE(ldx < (1LL << 30) && ldy < (1LL << 30), "spmm: row stride must be below 2^30 elements");
     SGL_REQUIRE(mode == SGLB200_MODE_FAST || mode == SGLB200_MODE_EXACT, "spmm: unknown mode %d", mode);
     Schedule *s = &g->fast;
     // accumulate starts every chain from the value already in Y: a cut row would race between the warp that reads
@@ -359,17 +384,24 @@ int spmm_launch(sglb200_graph *g, const float *X, int64_t ldx, float *Y, int64_t
     const dim3 grid((unsigned)((s->n_tiles + kWarpsPerBlock - 1) / kWarpsPerBlock), (unsigned)col_blocks, 1);
     const bool acc = accumulate != 0;
     cudaError_t e = cudaSuccess;
-#define SGL_SHAPE(V, L, UU) \
-    if (vec == V && vpl == L) e = launch_flat<V, L, UU>(p, acc, grid, stream)
-    SGL_SHAPE(4, 1, 8);
-    else SGL_SHAPE(4, 2, 4);
-    else SGL_SHAPE(4, 4, 2);
-    else SGL_SHAPE(2, 1, 8);
-    else SGL_SHAPE(2, 2, 4);
-    else SGL_SHAPE(2, 4, 2);
-    else SGL_SHAPE(1, 1, 8);
-    else SGL_SHAPE(1, 2, 8);
-    else SGL_SHAPE(1, 4, 4);
+#define SGL_SHAPE(V, L, UU, MB) \
+    if (vec == V && vpl == L) e = launch_flat<V, L, UU, MB>(p, acc, grid, stream)
+    if (vec == 4 && vpl == 1) {
+        switch (spmm_variant()) {
+        case 1: e = launch_flat<4, 1, 8, 3>(p, acc, grid, stream); break;
+        case 2: e = launch_flat<4, 1, 4, 4>(p, acc, grid, stream); break;
+        case 4: e = launch_flat<4, 1, 16, 2>(p, acc, grid, stream); break;
+        default: e = launch_flat<4, 1, 4, 5>(p, acc, grid, stream); break;  // measured best on B200 (profiles/)
+        }
+    }
+    else SGL_SHAPE(4, 2, 4, 3);
+    else SGL_SHAPE(4, 4, 2, 2);
+    else SGL_SHAPE(2, 1, 8, 4);
+    else SGL_SHAPE(2, 2, 4, 3);
+    else SGL_SHAPE(2, 4, 2, 2);
+    else SGL_SHAPE(1, 1, 8, 4);
+    else SGL_SHAPE(1, 2, 8, 3);
+    else SGL_SHAPE(1, 4, 4, 2);
     else {
         set_error("spmm: no kernel shape for vec=%d vpl=%d", vec, vpl);
         return SGLB200_ERR_INVALID;

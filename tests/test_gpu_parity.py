@@ -329,7 +329,7 @@ def test_arxiv_shape_properties():
     op0 = LaplacianGraphOp(3, r=0.0)
     ones = np.ones((n, 4), dtype=np.float32)
     for h in op0.propagate(adj, ones):
-        np.testing.assert_allclose(h.numpy(), 1.0, rtol=0, atol=2e-6)
+        np.testing.assert_allclose(h.numpy(), 1.0, rtol=0, atol=3e-5)   # deg terms of fp32 rounding on hub rows
     # (3) linearity: A(2x + y) == 2 Ax + Ay within fp32 rounding
     csr = CsrOperator.from_scipy(a)
     xd = torch.from_numpy(x).cuda()
