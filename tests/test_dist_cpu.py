@@ -1,0 +1,109 @@
+"""CPU tests (gloo, world_size 2 and 3): the 1-D row partition, the halo / all-gather exchange plans and the hop loop
+of sgl_b200.dist, with the oracle's C hop injected as the local kernel (the CUDA kernel is covered by -m gpu tests)."""
+import os
+import socket
+
+import numpy as np
+import pytest
+import scipy.sparse as sp
+import torch
+import torch.distributed as dist
+import torch.multiprocessing as mp
+
+from oracle import sgap_oracle as O
+from sgl_b200.dist import DistOperator, build_plan, exchange_volume_bytes, partition_rows
+
+
+def _graph(seed=0, n=600, m=5000):
+    rng = np.random.default_rng(seed)
+    rows = rng.integers(0, n, m)
+    cols = (rng.zipf(1.3, m) - 1) % n
+    r2, c2 = np.concatenate([rows, cols]), np.concatenate([cols, rows])
+    adj = sp.csr_matrix((np.ones(r2.size, dtype=np.float32), (r2, c2)), shape=(n, n))
+    return O.laplacian_adj(adj, 0.5)
+
+
+def test_partition_balances_work_and_covers_rows():
+    a = _graph()
+    for world in (1, 2, 3, 8):
+        b = partition_rows(a.indptr, world)
+        assert b[0] == 0 and b[-1] == a.shape[0] and np.all(np.diff(b) >= 0) and len(b) == world + 1
+        work = np.diff(a.indptr[b]) + 4 * np.diff(b)
+        assert work.max() <= work.mean() * 1.5 + a.indptr[1:].max()
+
+
+def test_plans_renumber_columns_consistently():
+    a = _graph(1)
+    world = 4
+    x = np.random.default_rng(2).standard_normal((a.shape[0], 8)).astype(np.float32)
+    ref = O.spmm_hop(a, x, "fma")
+    bounds = partition_rows(a.indptr, world)
+    for mode in ("halo", "allgather"):
+        plans = [build_plan(a.indptr, a.indices, a.data, a.shape[1], world, r, mode) for r in range(world)]
+        for p in plans:
+            lo, hi = bounds[p.rank], bounds[p.rank + 1]
+            ext = np.zeros((p.n_ext, 8), dtype=np.float32)
+            if mode == "halo":
+                ext[:p.n_local] = x[lo:hi]
+                pos = p.n_local
+                for q in range(world):      # what the all-to-all would deliver: rows q sends to p, in q's send order
+                    rows_q = plans[q].send_rows[p.rank] + bounds[q]
+                    assert len(rows_q) == p.recv_counts[q]
+                    ext[pos:pos + len(rows_q)] = x[rows_q]
+                    pos += len(rows_q)
+                assert pos == p.n_ext
+            else:
+                for q in range(world):
+                    ext[q * p.max_rows:q * p.max_rows + (bounds[q + 1] - bounds[q])] = x[bounds[q]:bounds[q + 1]]
+            y = np.zeros((p.n_local, 8), dtype=np.float32)
+            O._lib().oracle_spmm_f32_fma_i64(y, p.data, p.indices, p.indptr, ext, p.n_local, 8)
+            assert np.array_equal(y, ref[lo:hi])        # storage order is unchanged: bit-exact
+        halo = sum(exchange_volume_bytes(p, 8) for p in plans) if mode == "halo" else None
+        if halo is not None:
+            assert halo <= (world - 1) * a.shape[0] * 8 * 4
+
+
+def _free_port():
+    s = socket.socket()
+    s.bind(("127.0.0.1", 0))
+    port = s.getsockname()[1]
+    s.close()
+    return port
+
+
+def _worker(rank, world, port, mode, K, d, out_dir):
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        a = _graph(3)
+        x = np.random.default_rng(4).standard_normal((a.shape[0], d)).astype(np.float32)
+        plan = build_plan(a.indptr, a.indices, a.data, a.shape[1], world, rank, mode)
+
+        def oracle_hop(x_ext, out):          # checker kernel standing in for sglb200_spmm on the CPU
+            y = np.zeros((plan.n_local, d), dtype=np.float32)
+            O._lib().oracle_spmm_f32_fma_i64(y, plan.data, plan.indices, plan.indptr,
+                                             np.ascontiguousarray(x_ext.numpy()), plan.n_local, d)
+            out.copy_(torch.from_numpy(y))
+
+        op = DistOperator(plan, local_hop=oracle_hop)
+        lo, hi = plan.bounds[rank], plan.bounds[rank + 1]
+        hops = op.propagate(torch.from_numpy(x[lo:hi].copy()), K)
+        np.save(os.path.join(out_dir, f"hops_{mode}_{rank}.npy"), np.stack([h.numpy() for h in hops]))
+    finally:
+        dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("world", [2, 3])
+@pytest.mark.parametrize("mode", ["halo", "allgather"])
+def test_distributed_propagate_matches_single_process(tmp_path, world, mode):
+    K, d = 3, 12
+    port = _free_port()
+    mp.spawn(_worker, args=(world, port, mode, K, d, str(tmp_path)), nprocs=world, join=True)
+    a = _graph(3)
+    x = np.random.default_rng(4).standard_normal((a.shape[0], d)).astype(np.float32)
+    ref = np.stack(O.propagate(a, x, K, "fma"))
+    bounds = partition_rows(a.indptr, world)
+    for r in range(world):
+        got = np.load(tmp_path / f"hops_{mode}_{r}.npy")
+        assert np.array_equal(got, ref[:, bounds[r]:bounds[r + 1]])

@@ -343,3 +343,58 @@ def test_arxiv_shape_properties():
     assert torch.equal(e1, e2)
     assert_close_1e5(csr.spmm(xd, mode="fast").cpu().numpy(), e1.cpu().numpy())
     csr.close()
+
+
+# --------------------------------------------------------------------------------------------------------------
+# f2: A^ built on the device; e: the row-partitioned operator on CUDA
+# --------------------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("path", golden_graph_files(), ids=lambda p: os.path.basename(p)[6:-4])
+@pytest.mark.parametrize("tag,kind,r,alpha", GRAPH_TAGS)
+def test_device_built_adjacency_matches_goldens(path, tag, kind, r, alpha):
+    z, adj = load_graph(path)
+    K = z[tag + "_hops_fma"].shape[0] - 1
+    op = LaplacianGraphOp(K, r=r) if kind == "lap" else PprGraphOp(K, r=r, alpha=alpha)
+    op.mode, op.build_on = "exact", "device"
+    hops = op.propagate(_scipy_adj(adj), z["x"].copy())
+    got = np.stack([h.numpy() for h in hops])
+    a = op._adj                                                          # lazily downloaded scipy view
+    assert np.array_equal(a.indptr, z[tag + "_norm_indptr"]) and np.array_equal(a.indices, z[tag + "_norm_indices"])
+    if "weighted" in path:
+        assert np.array_equal(a.data.astype(np.float32), z[tag + "_norm_data"].astype(np.float32))
+    else:
+        assert np.array_equal(a.data, z[tag + "_norm_data"])
+    assert np.array_equal(got, z[tag + "_hops_fma"])
+
+
+def test_device_builder_larger_random_vs_oracle():
+    from sgl_b200.graph_build import operator_from_scipy_device, values_from_parts
+    rng = np.random.default_rng(31)
+    n = 5000
+    adj = random_graph(rng, n, 60000, skew=1.2)
+    for (r, alpha) in [(0.5, None), (0.3, 0.15)]:
+        ref = O.laplacian_adj(adj, r) if alpha is None else O.ppr_adj(adj, r, alpha)
+        op = operator_from_scipy_device(adj, r=r, alpha=alpha)
+        assert np.array_equal(op.parts["indptr"].cpu().numpy(), ref.indptr)
+        assert np.array_equal(op.parts["indices"].cpu().numpy(), ref.indices)
+        assert np.array_equal(values_from_parts(op.parts).cpu().numpy(), ref.data)
+        x = rng.standard_normal((n, 64)).astype(np.float32)
+        y = op.spmm(torch.from_numpy(x).cuda(), mode="exact").cpu().numpy()     # values written by the CUDA value pass
+        assert np.array_equal(y, O.spmm_hop(ref, x, "fma"))
+        op.close()
+
+
+def test_row_partition_single_rank_on_cuda():
+    """world = 1 degenerates to the single-GPU operator; exercises DistOperator's CUDA path without NCCL."""
+    from sgl_b200.dist import DistOperator, build_plan
+    rng = np.random.default_rng(37)
+    n, d, K = 2000, 128, 3
+    a = O.laplacian_adj(random_graph(rng, n, 15000), 0.5)
+    x = rng.standard_normal((n, d)).astype(np.float32)
+    ref = O.propagate(a, x, K, "fma")
+    for mode in ("halo", "allgather"):
+        plan = build_plan(a.indptr, a.indices, a.data, n, 1, 0, mode)
+        op = DistOperator(plan, mode="exact")
+        hops = op.propagate(torch.from_numpy(x).cuda(), K)
+        for k in range(K + 1):
+            assert np.array_equal(hops[k].cpu().numpy(), ref[k])
+        op.close()

@@ -142,3 +142,30 @@ def test_iterate_learnable_matches_reference(message_golden):
         op._learnable_weight.weight.copy_(torch.from_numpy(g["iter_w"]))
         op._learnable_weight.bias.copy_(torch.from_numpy(g["iter_b"]))
     np.testing.assert_allclose(op.aggregate(batch).detach().numpy(), g["iter_out"], rtol=1e-5, atol=1e-6)
+
+
+@pytest.mark.parametrize("path", golden_graph_files(), ids=lambda p: os.path.basename(p)[6:-4])
+@pytest.mark.parametrize("tag,kind,r,alpha", GRAPH_TAGS)
+def test_device_builder_passes_match_reference(path, tag, kind, r, alpha):
+    """graph_build.normalized_adjacency_device (torch sort / segment passes; run here on CPU tensors) must reproduce
+    the reference's CSR structure bit-exactly and, with the float64 value formula of sglb200_normalize_values
+    restated in numpy, its float64 values."""
+    from sgl_b200.graph_build import normalized_adjacency_device
+    z, adj = load_graph(path)
+    coo = _scipy_adj(adj).tocoo()
+    parts = normalized_adjacency_device(torch.from_numpy(coo.row.astype(np.int64)),
+                                        torch.from_numpy(coo.col.astype(np.int64)), adj.shape[0],
+                                        torch.from_numpy(coo.data.astype(np.float32)), r=r, alpha=alpha)
+    assert np.array_equal(parts["indptr"].numpy(), z[tag + "_norm_indptr"])
+    assert np.array_equal(parts["indices"].numpy(), z[tag + "_norm_indices"])
+    rows = np.repeat(np.arange(adj.shape[0]), np.diff(parts["indptr"].numpy()))
+    v = (parts["raw_w"].numpy() * parts["d_left"].numpy()[rows]) * parts["d_right"].numpy()[parts["indices"].numpy()]
+    if alpha is not None:
+        v = (1 - alpha) * v
+        v[rows == parts["indices"].numpy()] += alpha
+    ref = z[tag + "_norm_data"]
+    if "weighted" in path:   # non-integer weights: the float64 degree sum order (numpy pairwise) is not reproduced
+        np.testing.assert_allclose(v, ref, rtol=4e-16)
+        assert np.array_equal(v.astype(np.float32), ref.astype(np.float32))
+    else:
+        assert np.array_equal(v, ref)
