@@ -41,7 +41,8 @@ class GraphOp:
         self._prop_steps = prop_steps
         self._adj_value = None
         self._adj_parts = None
-        self._operator = None  # CsrOperator of the last propagate call
+        self._operator = None  # CsrOperator of the last propagate / prepare call
+        self._prepared_for = None
 
     @property
     def _adj(self):
@@ -61,7 +62,49 @@ class GraphOp:
     def _norm_spec(self):
         return None
 
+    def prepare(self, adj):
+        """Optional: build A^ and make it resident in HBM once; later propagate(adj, ...) calls with the SAME adjacency
+        object skip normalisation and upload (the reference rebuilds A^ on every call, base_op.py:20 -- its label-use
+        task calls preprocess every epoch, tasks/node_classification_with_label_use.py:79).  Returns self."""
+        if not isinstance(adj, (sp.csr_matrix, sp.coo_matrix)):
+            raise TypeError("The adjacency matrix must be a scipy.sparse.coo_matrix/csr_matrix!")
+        require_cuda()
+        if self._operator is not None:
+            self._operator.close()
+        spec = self._norm_spec() if self.build_on == "device" else None
+        if spec is not None:
+            from ..graph_build import operator_from_scipy_device
+            self._operator = operator_from_scipy_device(adj, r=spec[0], alpha=spec[1])
+            self._adj_value, self._adj_parts = None, self._operator.parts
+        else:
+            self._adj = self._construct_adj(adj)
+            self._operator = CsrOperator.from_scipy(self._adj)
+        self._prepared_for = adj
+        return self
+
+    def propagate_device(self, adj, feature, concat=False):
+        """Like propagate but returns the K+1 slabs as CUDA tensors regardless of `output_device` (used by the fused
+        preprocess of sgl_b200.sgap so that only the aggregated result crosses PCIe)."""
+        if getattr(self, "_prepared_for", None) is not adj or self._operator is None:
+            self.prepare(adj)
+        if feature.shape[0] != self._operator.shape[1]:
+            raise ValueError("Dimension mismatch detected for the adjacency and the feature matrix!")
+        if isinstance(feature, np.ndarray):
+            if feature.dtype != np.float32:
+                raise TypeError("The feature matrix must be a float32 numpy.ndarray!")
+            feature = torch.from_numpy(feature)
+        x = feature.detach().to(dtype=torch.float32).to(self._operator.device, non_blocking=True)
+        return self._operator.propagate(x, self._prop_steps, mode=self.mode, concat=concat)
+
     def propagate(self, adj, feature):
+        if getattr(self, "_prepared_for", None) is adj and self._operator is not None \
+                and isinstance(feature, (np.ndarray, Tensor)) and feature.shape[0] == self._operator.shape[1]:
+            hops = self.propagate_device(adj, feature)
+            if self.output_device == "cuda":
+                return hops
+            first = torch.from_numpy(feature) if isinstance(feature, np.ndarray) else feature.detach().float().cpu()
+            return [first] + [h.cpu() for h in hops[1:]]
+        self._prepared_for = None
         spec = self._norm_spec() if self.build_on == "device" else None
         if spec is not None and isinstance(adj, sp.csr_matrix) and isinstance(feature, (np.ndarray, Tensor)) \
                 and adj.shape[1] == feature.shape[0]:

@@ -35,14 +35,34 @@ class BaseSGAPModel(nn.Module):
         self._processed_feature = None
         self._pre_msg_learnable = False
 
+    # fused preprocess: hop slabs stay in HBM, the aggregation runs on them there, and only what forward() consumes
+    # crosses PCIe (the aggregated [N, d'] matrix for fixed combiners; nothing for learnable ones, whose K+1 slabs
+    # stay resident and are gathered per mini-batch on the device).  Set to False for the reference's exact data flow
+    # (K+1 CPU tensors in _processed_feat_list).
+    fused_preprocess = True
+    feature_device = "cpu"   # where _processed_feature lives after a fused preprocess ("cpu" like the reference | "cuda")
+
     def preprocess(self, adj, feature):
         """reference base_model.py:23-36"""
         if self._pre_graph_op is None:
             self._pre_msg_learnable = False
             self._processed_feature = feature
             return
-        self._processed_feat_list = self._pre_graph_op.propagate(adj, feature)
         self._pre_msg_learnable = self._pre_msg_op.aggr_type in _LEARNABLE
+        if self.fused_preprocess and hasattr(self._pre_graph_op, "propagate_device"):
+            hops = self._pre_graph_op.propagate_device(adj, feature)
+            self._processed_feat_list = hops                       # CUDA tensors
+            if not self._pre_msg_learnable:
+                out = self._pre_msg_op.aggregate(hops)
+                if self.feature_device == "cpu":
+                    host = torch.empty(out.shape, dtype=out.dtype, pin_memory=True)
+                    host.copy_(out, non_blocking=True)
+                    torch.cuda.current_stream().synchronize()
+                    out = host
+                    self._processed_feat_list = None               # the slabs are not needed again: free the HBM
+                self._processed_feature = out
+            return
+        self._processed_feat_list = self._pre_graph_op.propagate(adj, feature)
         if not self._pre_msg_learnable:
             self._processed_feature = self._pre_msg_op.aggregate(self._processed_feat_list)
 

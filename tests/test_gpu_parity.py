@@ -398,3 +398,61 @@ def test_row_partition_single_rank_on_cuda():
         for k in range(K + 1):
             assert np.array_equal(hops[k].cpu().numpy(), ref[k])
         op.close()
+
+
+# --------------------------------------------------------------------------------------------------------------
+# a14: the SGAP model glue (preprocess / forward contract) on top of the path
+# --------------------------------------------------------------------------------------------------------------
+def test_sgap_models_preprocess_and_forward():
+    from sgl_b200 import sgap
+    rng = np.random.default_rng(41)
+    n, d, K = 1500, 32, 3
+    adj = random_graph(rng, n, 12000)
+    x = rng.standard_normal((n, d)).astype(np.float32)
+    ref = O.propagate(O.laplacian_adj(adj, 0.5), x, K, "fma")
+    cases = [(sgap.SGC(K, d, 4), ref[K]), (sgap.SSGC(K, d, 4), O.combine_mean(ref, 0, K + 1)),
+             (sgap.GBP(K, d, 4, 16, 2), O.combine_weighted(ref, O.alpha_weights(K + 1, 0.85, 0, K + 1), 0, K + 1)),
+             (sgap.SIGN(K, d, 4, 16, 2), O.combine_concat(ref, 0, K + 1))]
+    for fused in (True, False):
+        for model, want in cases:
+            model.fused_preprocess = fused
+            model._pre_graph_op.mode = "exact"
+            model.preprocess(adj, x)
+            feat = model._processed_feature
+            assert isinstance(feat, torch.Tensor) and not feat.is_cuda and model._pre_msg_learnable is False
+            assert np.array_equal(feat.numpy(), want), type(model).__name__
+            out = model.model_forward(range(10, 50), "cuda")
+            assert out.shape[0] == 40 and out.is_cuda
+    nafs = sgap.NAFS(K, d, d)
+    nafs._pre_graph_op.mode = "exact"
+    nafs.preprocess(adj, x)
+    np.testing.assert_allclose(nafs._processed_feature.numpy(), O.combine_osd(ref), rtol=3e-6, atol=3e-6)
+    # learnable aggregator: slabs stay resident on the device, forward gathers there
+    gamlp = sgap.GAMLP(K, d, 5, 16, 2).cuda()
+    gamlp._pre_graph_op.mode = "exact"
+    gamlp.preprocess(adj, x)
+    assert gamlp._pre_msg_learnable and all(h.is_cuda for h in gamlp._processed_feat_list)
+    for k in range(K + 1):
+        assert np.array_equal(gamlp._processed_feat_list[k].cpu().numpy(), ref[k])
+    idx = torch.arange(0, 300, 3)
+    out = gamlp.model_forward(idx, "cuda")
+    assert out.shape == (100, 5)
+    out.sum().backward()
+    # prepared adjacency is reused for the same object and rebuilt for another
+    g = gamlp._pre_graph_op
+    handle = g._operator
+    gamlp.preprocess(adj, x)
+    assert g._operator is handle
+    gamlp.preprocess(adj.copy(), x)
+    assert g._operator is not handle
+    # postprocess path (softmax -> propagate -> aggregate) with a post graph op
+    from sgl_b200.operators.graph_op import PprGraphOp
+    from sgl_b200.operators.message_op import LastMessageOp
+    sgc = sgap.SGC(K, d, 4)
+    sgc._post_graph_op, sgc._post_msg_op = PprGraphOp(2, r=0.5, alpha=0.3), LastMessageOp()
+    sgc._post_graph_op.mode = "exact"
+    logits = torch.from_numpy(rng.standard_normal((n, 4)).astype(np.float32))
+    got = sgc.postprocess(adj, logits)
+    soft = torch.softmax(logits, dim=1).numpy()
+    want = O.propagate(O.ppr_adj(adj, 0.5, 0.3), soft, 2, "fma")[-1]
+    assert np.array_equal(got.numpy(), want)
