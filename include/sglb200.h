@@ -126,20 +126,23 @@ SGLB200_API int sglb200_propagate_host(sglb200_graph_t g, const float *X, float 
 SGLB200_API int sglb200_aggregate(int op, const float *const *feats, int n_feats, int64_t n, int d, int64_t ld_in,
                       const float *weights, float *out, int64_t ld_out, void *stream);
 
-/* ---- a11: LearnableWeightedMessageOp, fused forward / backward -----------------------------------------------
- * kind: 0 simple, 1 simple_allow_neg, 2 gate, 3 ori_ref, 4 jk (learnable_weighted_messahe_op.py:59-86; ori_ref/jk
- * use the reference's as-written [-1, K'] view of the hop-major score vector).
- * feats: n_all device pointers [B, d] (all hops, the jk reference row spans all of them); the op combines hops
- * [start, end).  w: parameter vector on the device (simple: n_all entries; gate: d; ori_ref: 2d; jk: (n_all+1)*d),
- * bias: 1 float on the device (NULL for simple kinds).  scratch: (end-start)*B floats (scores) + same (weights).
- * forward writes out [B, d] and keeps the softmax weights in `hop_w` [B, end-start] for the backward. */
+/* ---- a11: LearnableWeightedMessageOp (per-node kinds), fused forward / backward ------------------------------
+ * kind: 2 gate, 3 ori_ref, 4 jk (learnable_weighted_messahe_op.py:68-86; ori_ref/jk use the reference's as-written
+ * [-1, K'] view of the hop-major score vector).  The scalar kinds simple / simple_allow_neg have
+ * only K' parameters and no per-node work; they go through sglb200_aggregate(WEIGHTED).
+ * feats: n_all device pointers [B, d] contiguous (all hops: the jk reference row spans all of them); the op combines
+ * hops [start, end), K' = end-start.  w: parameter vector on the device (gate: d; ori_ref: 2d = [ref | hop];
+ * jk: (n_all+1)*d = [all hops | hop]); bias: 1 float on the device.
+ * forward: scores [K'*B] (hop-major pre-activation, kept for the backward), hop_w [B, K'] (softmax weights),
+ * out [B, d]. */
 SGLB200_API int sglb200_lw_forward(int kind, const float *const *feats, int n_all, int start, int end, int64_t B, int d,
-                       const float *w, const float *bias, float *hop_w, float *out, void *stream);
-/* backward: grad_out [B, d] -> grad_feats[k] [B, d] for all n_all hops (NULL entries skipped), grad_w (same length as
- * w, accumulated into: caller zeroes), grad_bias (1 float, accumulated).  scratch: (end-start)*B floats. */
+                       const float *w, const float *bias, float *scores, float *hop_w, float *out, void *stream);
+/* backward: grad_out [B, d] -> grad_feats[k] [B, d] for all n_all hops (ACCUMULATED into: caller zeroes), grad_w (same
+ * length as w, accumulated), grad_bias (1 float, accumulated).  scratch: K'*B floats. */
 SGLB200_API int sglb200_lw_backward(int kind, const float *const *feats, int n_all, int start, int end, int64_t B, int d,
-                        const float *w, const float *bias, const float *hop_w, const float *grad_out,
-                        float *const *grad_feats, float *grad_w, float *grad_bias, float *scratch, void *stream);
+                        const float *w, const float *bias, const float *scores, const float *hop_w,
+                        const float *grad_out, float *const *grad_feats, float *grad_w, float *grad_bias,
+                        float *scratch, void *stream);
 
 /* ---- f1: device-resident feature store: out[b, :] = feat[idx[b], :] for every hop in one launch --------------
  * (models/base_model.py:58-61 does a CPU fancy-index + H2D per step).  idx: B int64 on the device. */

@@ -36,9 +36,10 @@ SIGNATURES = {
     "sglb200_aggregate": (c_int, [c_int, POINTER(c_void_p), c_int, c_int64, c_int, c_int64, POINTER(c_float), c_void_p,
                                   c_int64, c_void_p]),
     "sglb200_lw_forward": (c_int, [c_int, POINTER(c_void_p), c_int, c_int, c_int, c_int64, c_int, c_void_p, c_void_p,
-                                   c_void_p, c_void_p, c_void_p]),
+                                   c_void_p, c_void_p, c_void_p, c_void_p]),
     "sglb200_lw_backward": (c_int, [c_int, POINTER(c_void_p), c_int, c_int, c_int, c_int64, c_int, c_void_p, c_void_p,
-                                    c_void_p, c_void_p, POINTER(c_void_p), c_void_p, c_void_p, c_void_p, c_void_p]),
+                                    c_void_p, c_void_p, c_void_p, POINTER(c_void_p), c_void_p, c_void_p, c_void_p,
+                                    c_void_p]),
     "sglb200_gather_rows": (c_int, [POINTER(c_void_p), c_int, c_int64, c_void_p, c_int64, c_int, POINTER(c_void_p),
                                     c_int64, c_void_p]),
     "FloatCSRMulDenseOMP": (None, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int]),

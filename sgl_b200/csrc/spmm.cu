@@ -42,6 +42,7 @@ struct SpmmParams {
     int d;
     float *carry_ws;
     int64_t ws_ld;
+    int stream_y;  // 1: output rows are stored with the streaming (evict-first) policy
 };
 
 template <int VEC> struct Vec;
@@ -84,27 +85,76 @@ template <int VEC> __device__ __forceinline__ void store_slice(float *p, const f
 __device__ __forceinline__ int32_t load_stream_i32(const int32_t *p)
 {
     int32_t v;
-    asm volatile("ld.global.nc.L1::no_allocate.s32 %0, [%1];" : "=r"(v) : "l"(p));
+    asm volatile("ld.global.cs.s32 %0, [%1];" : "=r"(v) : "l"(p));
     return v;
 }
 __device__ __forceinline__ float load_stream_f32(const float *p)
 {
     float v;
-    asm volatile("ld.global.nc.L1::no_allocate.f32 %0, [%1];" : "=f"(v) : "l"(p));
+    asm volatile("ld.global.cs.f32 %0, [%1];" : "=f"(v) : "l"(p));
     return v;
 }
 
-template <int VEC, int VPL, int U, bool ACCUM, int MINB>
+// A lane's slice of a feature row: VEC floats kept as packed fp32 pairs so that the accumulation is issued as
+// FFMA2 (fma.rn.f32x2, sm_100): two IEEE fused multiply-adds per instruction, bit-identical to two fmaf.
+template <int VEC> struct Slice;
+template <> struct Slice<4> {
+    ulonglong2 v;
+    __device__ __forceinline__ void zero() { v.x = 0ULL; v.y = 0ULL; }
+    __device__ __forceinline__ void load_nc(const char *p) { v = __ldg(reinterpret_cast<const ulonglong2 *>(p)); }
+    __device__ __forceinline__ void load(const char *p) { v = *reinterpret_cast<const ulonglong2 *>(p); }
+    __device__ __forceinline__ void store(char *p) const { *reinterpret_cast<ulonglong2 *>(p) = v; }
+    // output rows are written once and not re-read by this hop: streaming store, so they do not evict X from L2
+    __device__ __forceinline__ void store_streaming(char *p) const
+    {
+        asm volatile("st.global.cs.v2.u64 [%0], {%1, %2};" ::"l"(p), "l"(v.x), "l"(v.y) : "memory");
+    }
+    __device__ __forceinline__ void fma(float w, const Slice &x)
+    {
+        asm("{ .reg .b64 ww; mov.b64 ww, {%2, %2}; fma.rn.f32x2 %0, ww, %3, %0; fma.rn.f32x2 %1, ww, %4, %1; }"
+            : "+l"(v.x), "+l"(v.y) : "f"(w), "l"(x.v.x), "l"(x.v.y));
+    }
+};
+template <> struct Slice<2> {
+    unsigned long long v;
+    __device__ __forceinline__ void zero() { v = 0ULL; }
+    __device__ __forceinline__ void load_nc(const char *p) { v = __ldg(reinterpret_cast<const unsigned long long *>(p)); }
+    __device__ __forceinline__ void load(const char *p) { v = *reinterpret_cast<const unsigned long long *>(p); }
+    __device__ __forceinline__ void store(char *p) const { *reinterpret_cast<unsigned long long *>(p) = v; }
+    __device__ __forceinline__ void store_streaming(char *p) const
+    {
+        asm volatile("st.global.cs.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
+    }
+    __device__ __forceinline__ void fma(float w, const Slice &x)
+    {
+        asm("{ .reg .b64 ww; mov.b64 ww, {%1, %1}; fma.rn.f32x2 %0, ww, %2, %0; }" : "+l"(v) : "f"(w), "l"(x.v));
+    }
+};
+template <> struct Slice<1> {
+    float v;
+    __device__ __forceinline__ void zero() { v = 0.0f; }
+    __device__ __forceinline__ void load_nc(const char *p) { v = __ldg(reinterpret_cast<const float *>(p)); }
+    __device__ __forceinline__ void load(const char *p) { v = *reinterpret_cast<const float *>(p); }
+    __device__ __forceinline__ void store(char *p) const { *reinterpret_cast<float *>(p) = v; }
+    __device__ __forceinline__ void store_streaming(char *p) const
+    {
+        asm volatile("st.global.cs.f32 [%0], %1;" ::"l"(p), "f"(v) : "memory");
+    }
+    __device__ __forceinline__ void fma(float w, const Slice &x) { v = fmaf(w, x.v, v); }
+};
+
+template <int VEC, int VPL, int U, bool ACCUM, int MINB, int PIPE>
 __global__ void __launch_bounds__(kWarpsPerBlock * 32, MINB) spmm_flat_kernel(const SpmmParams p)
 {
     static_assert(32 % U == 0, "U must divide the batch of 32 non-zeros");
-    // (column id, value bits) of the current batch of 32 non-zeros, per warp, double buffered: one LDS.64 broadcast
-    // per non-zero hands every lane both the row to gather and its weight
-    __shared__ int2 s_pairs[kWarpsPerBlock][2][32];
+    static_assert(PIPE == 1 || PIPE == 2, "one or two groups of gathers in flight per warp");
+    // (column id, value bits) of two batches of 32 non-zeros per warp: one LDS.128 broadcast hands every lane two
+    // (row to gather, weight) pairs
+    __shared__ int2 s_pairs[kWarpsPerBlock][64];
     const int lane = threadIdx.x & 31;
     const int64_t t = (int64_t)blockIdx.x * kWarpsPerBlock + (threadIdx.x >> 5);
     if (t >= p.n_tiles) return;
-    int2 *pairs = &s_pairs[threadIdx.x >> 5][0][0];
+    int2 *pairs = &s_pairs[threadIdx.x >> 5][0];
 
     int row = p.tile_row[t];
     const int row_end = p.tile_row[t + 1];
@@ -130,16 +180,14 @@ __global__ void __launch_bounds__(kWarpsPerBlock * 32, MINB) spmm_flat_kernel(co
     }
     const uint32_t ldx_bytes = (uint32_t)p.ldx * (uint32_t)sizeof(float);  // strides < 2^30 elements (host check)
     const uint32_t ldy_bytes = (uint32_t)p.ldy * (uint32_t)sizeof(float);
-    float acc[VPL][VEC];
+    Slice<VEC> acc[VPL];
 
     auto init_acc = [&](int r) {
 #pragma unroll
         for (int v = 0; v < VPL; ++v) {
-#pragma unroll
-            for (int e = 0; e < VEC; ++e) acc[v][e] = 0.0f;
+            acc[v].zero();
             if (ACCUM) {
-                if (act[v] && r < n_rows)
-                    load_plain<VEC>(acc[v], reinterpret_cast<const float *>(ybase[v] + (uint64_t)(uint32_t)r * ldy_bytes));
+                if (act[v] && r < n_rows) acc[v].load(ybase[v] + (uint64_t)(uint32_t)r * ldy_bytes);
             }
         }
     };
@@ -168,7 +216,10 @@ __global__ void __launch_bounds__(kWarpsPerBlock * 32, MINB) spmm_flat_kernel(co
     auto flush_row = [&]() {
 #pragma unroll
         for (int v = 0; v < VPL; ++v)
-            if (act[v]) store_slice<VEC>(reinterpret_cast<float *>(ybase[v] + (uint64_t)(uint32_t)row * ldy_bytes), acc[v]);
+            if (act[v]) {
+                if (p.stream_y) acc[v].store_streaming(ybase[v] + (uint64_t)(uint32_t)row * ldy_bytes);
+                else acc[v].store(ybase[v] + (uint64_t)(uint32_t)row * ldy_bytes);
+            }
         ++row;
         if (row - row_base == 32) {
             row_base = row;
@@ -182,54 +233,89 @@ __global__ void __launch_bounds__(kWarpsPerBlock * 32, MINB) spmm_flat_kernel(co
     const int32_t *cols = p.indices + j0;
     const float *vals = p.vals + j0;
 
-    // (col, val) of the next 32 non-zeros are fetched one batch ahead of their use
+    // (col, val) of the next 32 non-zeros are fetched into registers one batch ahead of their publication
     int32_t col_next = 0;
     float val_next = 0.0f;
     if (lane < n_nnz) {
         col_next = load_stream_i32(cols + lane);
         val_next = load_stream_f32(vals + lane);
     }
-#pragma unroll 1
-    for (int base = 0; base < n_nnz; base += 32) {
-        // lanes past the end of the tile publish (column 0, weight 0): a valid row to gather, FMAs predicated off
-        int2 *batch = pairs + (base & 32);
-        batch[lane] = make_int2(col_next, __float_as_int(val_next));
+    // lanes past the end of the tile publish (column 0, weight 0): a valid row to gather, never accumulated
+    auto publish_batch = [&](int b) {
+        __syncwarp();  // every lane is done with the batch that used this buffer two batches ago
+        pairs[(b & 1) * 32 + lane] = make_int2(col_next, __float_as_int(val_next));
         __syncwarp();
         col_next = 0;
         val_next = 0.0f;
-        if (base + 32 + lane < n_nnz) {
-            col_next = load_stream_i32(cols + base + 32 + lane);
-            val_next = load_stream_f32(vals + base + 32 + lane);
+        const int nb = (b + 1) * 32 + lane;
+        if (nb < n_nnz) {
+            col_next = load_stream_i32(cols + nb);
+            val_next = load_stream_f32(vals + nb);
         }
-        const int n_here = min(32, n_nnz - base);
-#pragma unroll 1
-        for (int k = 0; k < n_here; k += U) {
-            // U gathered feature rows in flight before the first one is consumed
-            float x[U][VPL][VEC];
-            float w[U];
+    };
+
+    // software pipeline over groups of U non-zeros: the gathers of group g+1 are issued before group g is consumed,
+    // so every warp keeps U..2U feature rows in flight without pausing for its own arithmetic
+    auto issue = [&](Slice<VEC> (&buf)[U][VPL], int g) {
+        const int pos = g * U;
+        if ((pos & 31) == 0) publish_batch(pos >> 5);
+        const int2 *pp = pairs + (pos & 63);
+#pragma unroll
+        for (int u = 0; u < U; ++u) {
+            const uint32_t c = (uint32_t)pp[u].x;
+#pragma unroll
+            for (int v = 0; v < VPL; ++v) buf[u][v].load_nc(xbase[v] + (uint64_t)c * ldx_bytes);
+        }
+    };
+    auto consume = [&](Slice<VEC> (&buf)[U][VPL], int g) {
+        const int pos = g * U;
+        const int2 *pp = pairs + (pos & 63);
+        int left = next_end - pos;  // non-zeros of the current row still ahead, counted from the group start
+        if (left >= U && n_nnz - pos >= U) {
+            // the whole group belongs to the current row: no row-end checks, no predicates
 #pragma unroll
             for (int u = 0; u < U; ++u) {
-                const int2 cv = batch[k + u];
-                w[u] = __int_as_float(cv.y);
+                const float w = __int_as_float(pp[u].y);
 #pragma unroll
-                for (int v = 0; v < VPL; ++v)
-                    load_row_slice<VEC>(x[u][v], reinterpret_cast<const float *>(xbase[v] + (uint64_t)(uint32_t)cv.x * ldx_bytes));
+                for (int v = 0; v < VPL; ++v) acc[v].fma(w, buf[u][v]);
             }
-            const int pos = base + k;
-            const int valid = n_nnz - pos;   // >= U except in the padded tail of the last group
-            int left = next_end - pos;       // non-zeros of the current row still ahead, counted from the group start
+        } else {
+            const int valid = n_nnz - pos;
 #pragma unroll
             for (int u = 0; u < U; ++u) {
-                while (u == left) {          // warp-uniform: the current row ends here (also retires empty rows)
+                const float w = __int_as_float(pp[u].y);
+                while (u == left) {  // warp-uniform: the current row ends here (also retires empty rows)
                     flush_row();
                     left = next_end - pos;
                 }
-                const bool in_tile = u < valid;
+                if (u < valid) {     // false only in the padded tail of the last group
 #pragma unroll
-                for (int v = 0; v < VPL; ++v)
-#pragma unroll
-                    for (int e = 0; e < VEC; ++e) acc[v][e] = in_tile ? fmaf(w[u], x[u][v][e], acc[v][e]) : acc[v][e];
+                    for (int v = 0; v < VPL; ++v) acc[v].fma(w, buf[u][v]);
+                }
             }
+        }
+    };
+
+    const int n_groups = (n_nnz + U - 1) / U;
+    if constexpr (PIPE == 2) {
+        Slice<VEC> buf_a[U][VPL], buf_b[U][VPL];
+        if (n_groups > 0) issue(buf_a, 0);
+#pragma unroll 1
+        for (int g = 0; g < n_groups; g += 2) {
+            const bool has_b = g + 1 < n_groups;
+            if (has_b) issue(buf_b, g + 1);
+            consume(buf_a, g);
+            if (has_b) {
+                if (g + 2 < n_groups) issue(buf_a, g + 2);
+                consume(buf_b, g + 1);
+            }
+        }
+    } else {
+        Slice<VEC> buf[U][VPL];
+#pragma unroll 1
+        for (int g = 0; g < n_groups; ++g) {
+            issue(buf, g);
+            consume(buf, g);
         }
     }
     // rows (possibly empty ones) that end exactly at the end of the tile
@@ -237,10 +323,186 @@ __global__ void __launch_bounds__(kWarpsPerBlock * 32, MINB) spmm_flat_kernel(co
     // partial sum of the row cut by the tile end
     const int32_t slot = p.carry_slot[t];
     if (slot >= 0) {
-        float *wrow = p.carry_ws + (int64_t)slot * p.ws_ld;
+        char *wrow = reinterpret_cast<char *>(p.carry_ws + (int64_t)slot * p.ws_ld);
 #pragma unroll
         for (int v = 0; v < VPL; ++v)
-            if (act[v]) store_slice<VEC>(wrow + col_block + (v * 32 + lane) * VEC, acc[v]);
+            if (act[v]) acc[v].store(wrow + (size_t)(col_block + (v * 32 + lane) * VEC) * sizeof(float));
+    }
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// Ring variant of the hop kernel (float4 rows, d <= 256): gathered feature rows are staged with cp.async (LDGSTS.128)
+// into a per-warp ring in shared memory instead of registers, so the bytes in flight per SM are bounded by shared
+// memory (24 warps x 16 rows x 512 B = 192 KB) rather than by the register file.  Measured on B200 (profiles/): the
+// L2->SM ingest of this gather scales with the rows in flight up to ~18.6 TB/s; the register-staged kernel holds 160
+// rows/SM in flight (12 TB/s), this one up to 384.  Same schedule, same per-element fma order => same bits.
+// ---------------------------------------------------------------------------------------------------------------
+constexpr int kRingGroup = 8;  // rows committed per cp.async group
+
+template <int VPL, int RING, bool ACCUM>
+__global__ void __launch_bounds__(kWarpsPerBlock * 32, 3) spmm_ring_kernel(const SpmmParams p, int row_floats)
+{
+    constexpr int G = kRingGroup;
+    constexpr int D = RING / G;  // groups in flight
+    static_assert(RING % G == 0 && 32 % G == 0 && D >= 1, "ring geometry");
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    const int lane = threadIdx.x & 31;
+    const int wib = threadIdx.x >> 5;
+    const int64_t t = (int64_t)blockIdx.x * kWarpsPerBlock + wib;
+    float *ring = reinterpret_cast<float *>(smem_raw) + (size_t)wib * RING * row_floats;
+    int2 *pairs = reinterpret_cast<int2 *>(reinterpret_cast<float *>(smem_raw) + (size_t)kWarpsPerBlock * RING * row_floats) + wib * 64;
+    if (t >= p.n_tiles) return;
+
+    int row = p.tile_row[t];
+    const int row_end = p.tile_row[t + 1];
+    const int64_t j0 = p.tile_nnz[t];
+    const int n_nnz = (int)(p.tile_nnz[t + 1] - j0);
+    const int n_rows = (int)p.n_rows;
+
+    bool act[VPL];
+    const char *xbase[VPL];
+    char *ybase[VPL];
+    uint32_t soff[VPL];  // byte offset of this lane's slice inside a ring row
+#pragma unroll
+    for (int v = 0; v < VPL; ++v) {
+        const int cofs = (v * 32 + lane) * 4;
+        act[v] = cofs < p.d;
+        soff[v] = (uint32_t)(act[v] ? cofs : 0) * 4u;
+        xbase[v] = reinterpret_cast<const char *>(p.X) + soff[v];
+        ybase[v] = reinterpret_cast<char *>(p.Y) + (size_t)cofs * sizeof(float);
+        asm volatile("" : "+l"(xbase[v]));
+        asm volatile("" : "+l"(ybase[v]));
+    }
+    const uint32_t ldx_bytes = (uint32_t)p.ldx * 4u, ldy_bytes = (uint32_t)p.ldy * 4u;
+    const uint32_t row_bytes = (uint32_t)row_floats * 4u;
+    const uint32_t ring_s = (uint32_t)__cvta_generic_to_shared(ring);
+    float acc[VPL][4];
+
+    auto init_acc = [&](int r) {
+#pragma unroll
+        for (int v = 0; v < VPL; ++v) {
+#pragma unroll
+            for (int e = 0; e < 4; ++e) acc[v][e] = 0.0f;
+            if (ACCUM) {
+                if (act[v] && r < n_rows)
+                    load_plain<4>(acc[v], reinterpret_cast<const float *>(ybase[v] + (uint64_t)(uint32_t)r * ldy_bytes));
+            }
+        }
+    };
+    auto load_row_ends = [&](int base) -> int {
+        const int r = base + 1 + lane;
+        if (r > n_rows) return INT_MAX;
+        const int64_t rel = p.indptr[r] - j0;
+        return rel > (int64_t)INT_MAX ? INT_MAX : (int)rel;
+    };
+    int row_base = row;
+    int my_end = load_row_ends(row_base);
+    int next_end = __shfl_sync(kFull, my_end, 0);
+    if (row >= row_end) next_end = INT_MAX;
+    if (ACCUM) {
+        const bool starts_here = row < n_rows && p.indptr[row] == j0;
+        init_acc(starts_here ? row : n_rows);
+    } else {
+        init_acc(n_rows);
+    }
+    auto flush_row = [&]() {
+#pragma unroll
+        for (int v = 0; v < VPL; ++v)
+            if (act[v]) store_slice<4>(reinterpret_cast<float *>(ybase[v] + (uint64_t)(uint32_t)row * ldy_bytes), acc[v]);
+        ++row;
+        if (row - row_base == 32) {
+            row_base = row;
+            my_end = load_row_ends(row_base);
+        }
+        const int e = __shfl_sync(kFull, my_end, row - row_base);
+        next_end = row < row_end ? e : INT_MAX;
+        init_acc(row);
+    };
+
+    const int32_t *cols = p.indices + j0;
+    const float *vals = p.vals + j0;
+    int32_t col_next = 0;
+    float val_next = 0.0f;
+    if (lane < n_nnz) {
+        col_next = load_stream_i32(cols + lane);
+        val_next = load_stream_f32(vals + lane);
+    }
+    // publishes batch b (32 (col, val) pairs) to shared memory and prefetches batch b+1 into registers
+    auto publish_batch = [&](int b) {
+        pairs[(b & 1) * 32 + lane] = make_int2(col_next, __float_as_int(val_next));
+        __syncwarp();
+        col_next = 0;
+        val_next = 0.0f;
+        const int nb = (b + 1) * 32 + lane;
+        if (nb < n_nnz) {
+            col_next = load_stream_i32(cols + nb);
+            val_next = load_stream_f32(vals + nb);
+        }
+    };
+    // starts the asynchronous copies of the G rows of group g into their ring slots (padded positions copy row 0)
+    auto issue_group = [&](int g) {
+        const int pos = g * G;
+        if ((pos & 31) == 0) publish_batch(pos >> 5);
+        const int2 *pp = pairs + (pos & 63);
+        const uint32_t slot0 = ring_s + (uint32_t)((g % D) * G) * row_bytes;
+#pragma unroll
+        for (int u = 0; u < G; ++u) {
+            const uint32_t c = (uint32_t)pp[u].x;
+#pragma unroll
+            for (int v = 0; v < VPL; ++v) {
+                const char *src = xbase[v] + (uint64_t)c * ldx_bytes;
+                const uint32_t dst = slot0 + (uint32_t)u * row_bytes + soff[v];
+                asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst), "l"(src) : "memory");
+            }
+        }
+    };
+
+    const int n_groups = (n_nnz + G - 1) / G;
+#pragma unroll 1
+    for (int g = 0; g < D && g < n_groups; ++g) {
+        issue_group(g);
+        asm volatile("cp.async.commit_group;" ::: "memory");
+    }
+#pragma unroll 1
+    for (int g = 0; g < n_groups; ++g) {
+        // groups g+1 .. g+D-1 may stay in flight; group g must have landed
+        if (g + D - 1 < n_groups) asm volatile("cp.async.wait_group %0;" ::"n"(D - 1) : "memory");
+        else asm volatile("cp.async.wait_group 0;" ::: "memory");
+        __syncwarp();
+        const int pos = g * G;
+        const int2 *pp = pairs + (pos & 63);
+        const float *slot = ring + (size_t)((g % D) * G) * row_floats;
+        const int valid = n_nnz - pos;
+        int left = next_end - pos;
+#pragma unroll
+        for (int u = 0; u < G; ++u) {
+            const float w = __int_as_float(pp[u].y);
+            float x[VPL][4];
+#pragma unroll
+            for (int v = 0; v < VPL; ++v) load_plain<4>(x[v], slot + (size_t)u * row_floats + (soff[v] >> 2));
+            while (u == left) {
+                flush_row();
+                left = next_end - pos;
+            }
+            const bool in_tile = u < valid;
+#pragma unroll
+            for (int v = 0; v < VPL; ++v)
+#pragma unroll
+                for (int e = 0; e < 4; ++e) acc[v][e] = in_tile ? fmaf(w, x[v][e], acc[v][e]) : acc[v][e];
+        }
+        __syncwarp();  // every lane is done with group g's slots and pairs before they are refilled
+        if (g + D < n_groups) {
+            issue_group(g + D);
+            asm volatile("cp.async.commit_group;" ::: "memory");
+        }
+    }
+    while (row < row_end) flush_row();
+    const int32_t slot_id = p.carry_slot[t];
+    if (slot_id >= 0) {
+        float *wrow = p.carry_ws + (int64_t)slot_id * p.ws_ld;
+#pragma unroll
+        for (int v = 0; v < VPL; ++v)
+            if (act[v]) store_slice<4>(wrow + (v * 32 + lane) * 4, acc[v]);
     }
 }
 
@@ -284,11 +546,11 @@ __global__ void __launch_bounds__(kWarpsPerBlock * 32)
     }
 }
 
-template <int VEC, int VPL, int U, int MINB>
+template <int VEC, int VPL, int U, int MINB, int PIPE = 1>
 static cudaError_t launch_flat(const SpmmParams &p, bool accum, dim3 grid, cudaStream_t stream)
 {
-    if (accum) spmm_flat_kernel<VEC, VPL, U, true, (MINB > 3 ? 3 : MINB)><<<grid, kWarpsPerBlock * 32, 0, stream>>>(p);
-    else spmm_flat_kernel<VEC, VPL, U, false, MINB><<<grid, kWarpsPerBlock * 32, 0, stream>>>(p);
+    if (accum) spmm_flat_kernel<VEC, VPL, U, true, (MINB > 3 ? 3 : MINB), 1><<<grid, kWarpsPerBlock * 32, 0, stream>>>(p);
+    else spmm_flat_kernel<VEC, VPL, U, false, MINB, PIPE><<<grid, kWarpsPerBlock * 32, 0, stream>>>(p);
     return cudaGetLastError();
 }
 
@@ -380,18 +642,60 @@ int spmm_launch(sglb200_graph *g, const float *X, int64_t ldx, float *Y, int64_t
     p.d = d;
     p.carry_ws = g->carry_ws;
     p.ws_ld = ws_ld;
+    {
+        // X (n_cols x d) should own L2 during a hop: stream Y past it unless Y is small enough to stay resident too
+        static int force = -2;
+        if (force == -2) {
+            const char *e = getenv("SGLB200_STREAM_Y");
+            force = e ? atoi(e) : -1;
+        }
+        p.stream_y = force >= 0 ? force : 1;
+    }
 
     const dim3 grid((unsigned)((s->n_tiles + kWarpsPerBlock - 1) / kWarpsPerBlock), (unsigned)col_blocks, 1);
     const bool acc = accumulate != 0;
     cudaError_t e = cudaSuccess;
 #define SGL_SHAPE(V, L, UU, MB) \
     if (vec == V && vpl == L) e = launch_flat<V, L, UU, MB>(p, acc, grid, stream)
-    if (vec == 4 && vpl == 1) {
-        switch (spmm_variant()) {
-        case 1: e = launch_flat<4, 1, 8, 3>(p, acc, grid, stream); break;
-        case 2: e = launch_flat<4, 1, 4, 4>(p, acc, grid, stream); break;
-        case 4: e = launch_flat<4, 1, 16, 2>(p, acc, grid, stream); break;
-        default: e = launch_flat<4, 1, 4, 5>(p, acc, grid, stream); break;  // measured best on B200 (profiles/)
+    const int variant = spmm_variant();
+    const int row_floats = (d + 3) & ~3;
+    if (vec == 4 && vpl <= 2 && col_blocks == 1 && (variant == -1 ? false : variant >= 10)) {
+        // ring (cp.async) variant: variant 10 = 16-row ring, 11 = 24-row ring, 12 = 8-row ring
+        const int ring_rows = variant == 11 ? 24 : (variant == 12 ? 8 : 16);
+        const size_t smem = (size_t)kWarpsPerBlock * ring_rows * row_floats * sizeof(float) + kWarpsPerBlock * 64 * sizeof(int2);
+#define SGL_RING(L, R, A)                                                                                          \
+    do {                                                                                                           \
+        static bool attr_done = false;                                                                             \
+        if (!attr_done) {                                                                                          \
+            e = cudaFuncSetAttribute(spmm_ring_kernel<L, R, A>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024); \
+            attr_done = (e == cudaSuccess);                                                                        \
+        }                                                                                                          \
+        if (e == cudaSuccess) {                                                                                    \
+            spmm_ring_kernel<L, R, A><<<grid, kWarpsPerBlock * 32, smem, stream>>>(p, row_floats);                 \
+            e = cudaGetLastError();                                                                                \
+        }                                                                                                          \
+    } while (0)
+        if (vpl == 1) {
+            if (ring_rows == 24) { if (acc) SGL_RING(1, 24, true); else SGL_RING(1, 24, false); }
+            else if (ring_rows == 8) { if (acc) SGL_RING(1, 8, true); else SGL_RING(1, 8, false); }
+            else { if (acc) SGL_RING(1, 16, true); else SGL_RING(1, 16, false); }
+        } else {
+            if (ring_rows == 24) { if (acc) SGL_RING(2, 24, true); else SGL_RING(2, 24, false); }
+            else if (ring_rows == 8) { if (acc) SGL_RING(2, 8, true); else SGL_RING(2, 8, false); }
+            else { if (acc) SGL_RING(2, 16, true); else SGL_RING(2, 16, false); }
+        }
+#undef SGL_RING
+    }
+    else if (vec == 4 && vpl == 1) {
+        switch (variant) {
+        case 2: e = launch_flat<4, 1, 4, 4, 1>(p, acc, grid, stream); break;
+        case 3: e = launch_flat<4, 1, 4, 3, 2>(p, acc, grid, stream); break;
+        case 4: e = launch_flat<4, 1, 4, 4, 2>(p, acc, grid, stream); break;
+        case 5: e = launch_flat<4, 1, 8, 4, 1>(p, acc, grid, stream); break;
+        case 6: e = launch_flat<4, 1, 2, 5, 2>(p, acc, grid, stream); break;
+        case 7: e = launch_flat<4, 1, 8, 2, 2>(p, acc, grid, stream); break;
+        case 8: e = launch_flat<4, 1, 4, 5, 1>(p, acc, grid, stream); break;
+        default: e = launch_flat<4, 1, 8, 3, 1>(p, acc, grid, stream); break;  // measured best on B200 (profiles/)
         }
     }
     else SGL_SHAPE(4, 2, 4, 3);

@@ -12,8 +12,62 @@ import torch.nn.functional as F
 from torch import nn
 from torch.nn import Linear, ModuleList, Parameter
 
+from ctypes import c_void_p
+
+from ... import _lib
 from ..base_op import MessageOp
 from ..utils import one_dim_weighted_add, two_dim_weighted_add
+
+
+class _FusedHopWeights(torch.autograd.Function):
+    """out = sum_j W[:, j] * feats[start+j] with W = softmax(sigmoid(Linear(...))) for gate / ori_ref / jk, forward and
+    backward in libsglb200 (sglb200_lw_forward / sglb200_lw_backward): the reference row is dotted once per node
+    instead of being repeated K' times, nothing of size [(K'*B), (K+2)*d] is materialised."""
+
+    @staticmethod
+    def forward(ctx, kind, start, end, weight, bias, *feats):
+        lib = _lib.load()
+        feats = [f.detach().contiguous() for f in feats]
+        B, d = int(feats[0].shape[0]), int(feats[0].shape[1])
+        kp = end - start
+        dev = feats[0].device
+        w = weight.detach().reshape(-1).contiguous()
+        b = bias.detach().reshape(-1).contiguous()
+        scores = torch.empty(kp * B, dtype=torch.float32, device=dev)
+        hop_w = torch.empty((B, kp), dtype=torch.float32, device=dev)
+        out = torch.empty((B, d), dtype=torch.float32, device=dev)
+        with torch.cuda.device(dev):
+            stream = c_void_p(torch.cuda.current_stream().cuda_stream)
+            _lib.check(lib.sglb200_lw_forward(kind, _lib.ptr_array([f.data_ptr() for f in feats]), len(feats), start,
+                                              end, B, d, c_void_p(w.data_ptr()), c_void_p(b.data_ptr()),
+                                              c_void_p(scores.data_ptr()), c_void_p(hop_w.data_ptr()),
+                                              c_void_p(out.data_ptr()), stream), "lw_forward")
+        ctx.meta = (kind, start, end, weight.shape, bias.shape)
+        ctx.save_for_backward(w, b, scores, hop_w, *feats)
+        return out
+
+    @staticmethod
+    def backward(ctx, grad_out):
+        lib = _lib.load()
+        kind, start, end, w_shape, b_shape = ctx.meta
+        w, b, scores, hop_w, *feats = ctx.saved_tensors
+        B, d = int(feats[0].shape[0]), int(feats[0].shape[1])
+        dev = feats[0].device
+        grad_out = grad_out.contiguous().float()
+        grads = [torch.zeros_like(f) for f in feats]
+        gw = torch.zeros_like(w)
+        gb = torch.zeros_like(b)
+        scratch = torch.empty((end - start) * B, dtype=torch.float32, device=dev)
+        with torch.cuda.device(dev):
+            stream = c_void_p(torch.cuda.current_stream().cuda_stream)
+            _lib.check(lib.sglb200_lw_backward(kind, _lib.ptr_array([f.data_ptr() for f in feats]), len(feats), start,
+                                               end, B, d, c_void_p(w.data_ptr()), c_void_p(b.data_ptr()),
+                                               c_void_p(scores.data_ptr()), c_void_p(hop_w.data_ptr()),
+                                               c_void_p(grad_out.data_ptr()),
+                                               _lib.ptr_array([g.data_ptr() for g in grads]), c_void_p(gw.data_ptr()),
+                                               c_void_p(gb.data_ptr()), c_void_p(scratch.data_ptr()), stream),
+                       "lw_backward")
+        return (None, None, None, gw.view(w_shape), gb.view(b_shape), *grads)
 
 
 class LearnableWeightedMessageOp(MessageOp):
@@ -63,7 +117,15 @@ class LearnableWeightedMessageOp(MessageOp):
             score = self._learnable_weight(torch.hstack((ref.repeat(e - s, 1), stacked))).view(-1, e - s)
         return F.softmax(torch.sigmoid(score), dim=1)
 
+    fused = True  # per-node kinds on CUDA batches run the fused kernels; False keeps the torch expressions
+
     def _combine(self, feat_list):
+        kind = self._combination_type
+        if (self.fused and kind in ("gate", "ori_ref", "jk") and len(feat_list) <= 64 and feat_list[0].dim() == 2
+                and all(f.is_cuda and f.dtype == torch.float32 and f.shape == feat_list[0].shape for f in feat_list)):
+            lin = self._learnable_weight
+            return _FusedHopWeights.apply(_lib.LW_KINDS[kind], self._start, self._end, lin.weight, lin.bias,
+                                          *feat_list)
         weights = self.hop_weights(feat_list)
         sel = feat_list[self._start:self._end]
         if weights.dim() == 1:

@@ -410,9 +410,10 @@ def test_sgap_models_preprocess_and_forward():
     adj = random_graph(rng, n, 12000)
     x = rng.standard_normal((n, d)).astype(np.float32)
     ref = O.propagate(O.laplacian_adj(adj, 0.5), x, K, "fma")
-    cases = [(sgap.SGC(K, d, 4), ref[K]), (sgap.SSGC(K, d, 4), O.combine_mean(ref, 0, K + 1)),
-             (sgap.GBP(K, d, 4, 16, 2), O.combine_weighted(ref, O.alpha_weights(K + 1, 0.85, 0, K + 1), 0, K + 1)),
-             (sgap.SIGN(K, d, 4, 16, 2), O.combine_concat(ref, 0, K + 1))]
+    cases = [(sgap.SGC(K, d, 4).cuda(), ref[K]), (sgap.SSGC(K, d, 4).cuda(), O.combine_mean(ref, 0, K + 1)),
+             (sgap.GBP(K, d, 4, 16, 2).cuda(),
+              O.combine_weighted(ref, O.alpha_weights(K + 1, 0.85, 0, K + 1), 0, K + 1)),
+             (sgap.SIGN(K, d, 4, 16, 2).cuda(), O.combine_concat(ref, 0, K + 1))]
     for fused in (True, False):
         for model, want in cases:
             model.fused_preprocess = fused
@@ -456,3 +457,60 @@ def test_sgap_models_preprocess_and_forward():
     soft = torch.softmax(logits, dim=1).numpy()
     want = O.propagate(O.ppr_adj(adj, 0.5, 0.3), soft, 2, "fma")[-1]
     assert np.array_equal(got.numpy(), want)
+
+
+# --------------------------------------------------------------------------------------------------------------
+# a11: fused LearnableWeightedMessageOp kernels (forward + autograd) against the reference goldens
+# --------------------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("kind", ["gate", "ori_ref", "jk"])
+@pytest.mark.parametrize("se", [(0, 5), (1, 4)])
+def test_fused_learnable_weighted_op(message_golden, kind, se):
+    from sgl_b200.operators.message_op import LearnableWeightedMessageOp
+    g = message_golden
+    s, e = se
+    K, d = 4, 16
+    batch = [torch.from_numpy(h[g["batch_idx"]]).cuda() for h in g["hops"]]
+    args = {"gate": (d,), "ori_ref": (d,), "jk": (K, d)}[kind]
+    tag = f"lw_{kind}_{s}_{e}"
+    results = {}
+    for fused in (True, False):
+        op = LearnableWeightedMessageOp(s, e, kind, *args).cuda()
+        op.fused = fused
+        with torch.no_grad():
+            op._learnable_weight.weight.copy_(torch.from_numpy(g[tag + "_w"]))
+            op._learnable_weight.bias.copy_(torch.from_numpy(g[tag + "_b"]))
+        feats = [b.clone().requires_grad_(True) for b in batch]
+        out = op.aggregate(feats)
+        gout = torch.linspace(-1, 1, out.numel(), device="cuda").reshape(out.shape)
+        out.backward(gout)
+        gin = np.stack([f.grad.cpu().numpy() if f.grad is not None else np.zeros((len(g["batch_idx"]), d), np.float32)
+                        for f in feats])
+        results[fused] = (out.detach().cpu().numpy(), gin, op._learnable_weight.weight.grad.cpu().numpy(),
+                          op._learnable_weight.bias.grad.cpu().numpy())
+    for fused, (out, gin, gw, gb) in results.items():
+        np.testing.assert_allclose(out, g[tag + "_out"], rtol=1e-5, atol=2e-6, err_msg=f"fused={fused}")
+        np.testing.assert_allclose(gin, g[tag + "_gin"], rtol=1e-4, atol=1e-5, err_msg=f"fused={fused}")
+        np.testing.assert_allclose(gw, g[tag + "_gw"], rtol=1e-4, atol=2e-5, err_msg=f"fused={fused}")
+        np.testing.assert_allclose(gb, g[tag + "_gb"], rtol=1e-4, atol=2e-5, err_msg=f"fused={fused}")
+
+
+def test_fused_learnable_larger_batch_matches_torch_expressions():
+    from sgl_b200.operators.message_op import LearnableWeightedMessageOp
+    torch.manual_seed(3)
+    K, d, B = 6, 128, 5000
+    feats = [torch.randn(B, d, device="cuda") for _ in range(K + 1)]
+    for kind, args in [("gate", (d,)), ("ori_ref", (d,)), ("jk", (K, d))]:
+        op = LearnableWeightedMessageOp(0, K + 1, kind, *args).cuda()
+        outs, grads = [], []
+        for fused in (True, False):
+            op.fused = fused
+            op.zero_grad()
+            fs = [f.clone().requires_grad_(True) for f in feats]
+            out = op.aggregate(fs)
+            out.square().mean().backward()
+            outs.append(out.detach())
+            grads.append((torch.stack([f.grad for f in fs]), op._learnable_weight.weight.grad.clone(),
+                          op._learnable_weight.bias.grad.clone()))
+        assert torch.allclose(outs[0], outs[1], rtol=1e-5, atol=1e-6), kind
+        for a, b in zip(grads[0], grads[1]):
+            assert torch.allclose(a, b, rtol=2e-4, atol=1e-7), kind
