@@ -294,7 +294,18 @@ int sglb200_graph_create(sglb200_graph_t *out, int64_t n_rows, int64_t n_cols, i
     g->n_rows = n_rows;
     g->n_cols = n_cols;
     g->nnz = nnz;
-    g->tile_items = tile_items > 0 ? tile_items : 256;         // measured on B200: 256 items / warp,
+    if (tile_items > 0) {
+        g->tile_items = tile_items;
+    } else {
+        // measured on B200 (profiles/): 256 items per warp once the graph fills the chip; smaller graphs get
+        // proportionally smaller tiles so that every SM still holds ~48 warps' worth of tiles
+        const int64_t total = n_rows + nnz;
+        const int64_t per_warp = total / ((int64_t)g->sm_count * 48);
+        int64_t ti = ((per_warp + 31) / 32) * 32;
+        if (ti < 32) ti = 32;
+        if (ti > 256) ti = 256;
+        g->tile_items = (int)ti;
+    }
     g->split_threshold = split_threshold > 0 ? split_threshold : 64;  // rows above 64 non-zeros may be cut
     const cudaMemcpyKind kind = loc == SGLB200_HOST ? cudaMemcpyHostToDevice : cudaMemcpyDeviceToDevice;
     G_CHECK(cudaMalloc(&g->indptr, sizeof(int64_t) * (n_rows + 1)));
