@@ -54,6 +54,7 @@ def parse_args():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--exchange", default="halo", choices=["halo", "allgather"])
+    ap.add_argument("--chunks", type=int, default=4, help="row chunks the hop is pipelined over against its halo exchange")
     return ap.parse_args()
 
 
@@ -430,7 +431,7 @@ def run_dist(args):
     nnz = int(indptr[-1])
     del parts, vals
     torch.cuda.empty_cache()
-    plan = build_plan(indptr, indices, data, n, world, rank, args.exchange)
+    plan = build_plan(indptr, indices, data, n, world, rank, args.exchange, n_chunks=args.chunks)
     t_build = time.perf_counter() - t0
     op = DistOperator(plan, device=dev, mode=args.mode)
     lo, hi = int(plan.bounds[rank]), int(plan.bounds[rank + 1])
@@ -483,7 +484,7 @@ def run_dist(args):
         line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
                 "warmup": max(args.warmup, 3), "ms_per_step": 1e3 * total_s / args.steps, "higher_is_better": True,
                 "scaling": "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-                "config": dict(workload_config(name, n, nnz, d, K, args), exchange=args.exchange,
+                "config": dict(workload_config(name, n, nnz, d, K, args), exchange=args.exchange, chunks=args.chunks,
                                halo_recv_bytes_per_hop_max_rank=float(recv.item())),
                 "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak * world, "unit": "GB/s",
                              "frac": achieved / (peak * world), "traffic": None, "kernel": "spmm_flat_kernel",

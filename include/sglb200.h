@@ -110,6 +110,14 @@ SGLB200_API int sglb200_normalize_values(sglb200_graph_t g, const double *raw_w,
 SGLB200_API int sglb200_spmm(sglb200_graph_t g, const float *X, int64_t ldx, float *Y, int64_t ldy, int d, int mode,
                  int accumulate, void *stream);
 
+/* chunked hop for pipelining a hop against the halo exchange of a row partition:
+ * sglb200_graph_chunks splits the warp schedule of `mode` into n_chunks consecutive tile ranges and reports, per
+ * chunk, the tile bounds and the rows whose final value that chunk produces (row_bounds[c] .. row_bounds[c+1]-1);
+ * sglb200_spmm_tiles runs one such range (cut rows that finish inside it are folded before it returns to the stream). */
+SGLB200_API int sglb200_graph_chunks(sglb200_graph_t g, int mode, int n_chunks, int64_t *tile_bounds, int64_t *row_bounds);
+SGLB200_API int sglb200_spmm_tiles(sglb200_graph_t g, const float *X, int64_t ldx, float *Y, int64_t ldy, int d, int mode,
+                       int64_t tile_begin, int64_t tile_end, void *stream);
+
 /* ---- a1: K hops, device resident -----------------------------------------------------------------------------
  * hops[0..K] are K+1 device pointers to [n, d] slabs with row stride ld; hops[0] holds X on entry, hops[k] receives
  * A^^k X.  Slabs may be column blocks of one [n, (K+1)*d] concat buffer (ld = (K+1)*d).  Requires n_rows==n_cols. */

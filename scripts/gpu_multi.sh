@@ -7,9 +7,9 @@ nvidia-smi -L > $OUT/gpus.txt
 python -m pytest tests/test_dist_gpu.py -m gpu -x -q > $OUT/pytest_dist.log 2>&1; echo "pytest exit $?" >> $OUT/pytest_dist.log; tail -n 3 $OUT/pytest_dist.log
 for wl in $WL; do
   python bench.py --workload $wl --steps 5 --warmup 3 --no-cpu-baseline --no-e2e > $OUT/bench_${wl}_n1.json 2> $OUT/bench_${wl}_n1.err; echo "n1 $wl exit $?"
-  for ex in halo allgather; do
+  for ex in ${EXCH:-halo allgather}; do
     python -m torch.distributed.run --nnodes=1 --nproc-per-node $N --master-addr 127.0.0.1 --master-port 29511 \
-      bench.py --gpus $N --workload $wl --steps 5 --warmup 3 --exchange $ex > $OUT/bench_${wl}_n${N}_${ex}.json 2> $OUT/bench_${wl}_n${N}_${ex}.err
+      bench.py --gpus $N --workload $wl --steps 5 --warmup 3 --exchange $ex ${EXTRA} > $OUT/bench_${wl}_n${N}_${ex}.json 2> $OUT/bench_${wl}_n${N}_${ex}.err
     echo "n$N $wl $ex exit $?"
   done
 done

@@ -4,6 +4,8 @@
 #include <cuda_runtime.h>
 #include <stdint.h>
 
+#include <vector>
+
 #include "sglb200.h"
 
 namespace sglb200 {
@@ -42,6 +44,8 @@ struct Schedule {
     int32_t *run_row = nullptr;     // n_runs
     int64_t *run_base = nullptr;    // n_runs : first slot
     int32_t *run_len = nullptr;     // n_runs : consecutive slots
+    std::vector<int64_t> run_last_tile;  // host copy, sorted: tile that finishes the cut row of run r (runs are
+                                         // sorted by row, so a tile range maps to a contiguous run range)
 };
 
 }  // namespace sglb200

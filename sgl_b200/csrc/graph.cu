@@ -7,7 +7,9 @@
 #include <stdio.h>
 #include <string.h>
 
+#include <algorithm>
 #include <new>
+#include <vector>
 
 #include "common.cuh"
 
@@ -89,7 +91,7 @@ __device__ __forceinline__ int32_t carried_row(const int64_t *indptr, const int3
 __global__ void carry_runs_kernel(const int64_t *__restrict__ indptr, const int32_t *__restrict__ tile_row,
                                   const int64_t *__restrict__ tile_nnz, int64_t n_rows, int64_t n_tiles, int pass,
                                   unsigned long long *counts, int32_t *carry_slot, int32_t *run_row, int64_t *run_base,
-                                  int32_t *run_len)
+                                  int32_t *run_len, int64_t *run_head)
 {
     const int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (t >= n_tiles) return;
@@ -107,6 +109,7 @@ __global__ void carry_runs_kernel(const int64_t *__restrict__ indptr, const int3
         run_row[r] = row;
         run_base[r] = (int64_t)base;
         run_len[r] = (int32_t)len;
+        run_head[r] = t;
         for (int64_t u = 0; u < len; ++u) carry_slot[t + u] = (int32_t)(base + u);
     }
 }
@@ -143,7 +146,7 @@ int build_schedule(sglb200_graph *g, Schedule *s, int64_t split_threshold, cudaS
         SGL_CUDA_CHECK(cudaMemsetAsync(counts, 0, 4 * sizeof(unsigned long long), stream));
         const unsigned blocks = (unsigned)((n_tiles + threads - 1) / threads);
         carry_runs_kernel<<<blocks, threads, 0, stream>>>(g->indptr, s->tile_row, s->tile_nnz, g->n_rows, n_tiles, 0,
-                                                          counts, nullptr, nullptr, nullptr, nullptr);
+                                                          counts, nullptr, nullptr, nullptr, nullptr, nullptr);
         SGL_CUDA_CHECK(cudaGetLastError());
         unsigned long long h[4];
         SGL_CUDA_CHECK(cudaMemcpyAsync(h, counts, sizeof(h), cudaMemcpyDeviceToHost, stream));
@@ -155,10 +158,40 @@ int build_schedule(sglb200_graph *g, Schedule *s, int64_t split_threshold, cudaS
             SGL_CUDA_CHECK(cudaMalloc(&s->run_base, sizeof(int64_t) * s->n_runs));
             SGL_CUDA_CHECK(cudaMalloc(&s->run_len, sizeof(int32_t) * s->n_runs));
             g->bytes_resident += (size_t)s->n_runs * 16;
+            int64_t *run_head = nullptr;
+            SGL_CUDA_CHECK(cudaMalloc(&run_head, sizeof(int64_t) * s->n_runs));
             carry_runs_kernel<<<blocks, threads, 0, stream>>>(g->indptr, s->tile_row, s->tile_nnz, g->n_rows, n_tiles,
                                                               1, counts, s->carry_slot, s->run_row, s->run_base,
-                                                              s->run_len);
-            SGL_CUDA_CHECK(cudaGetLastError());
+                                                              s->run_len, run_head);
+            cudaError_t e = cudaGetLastError();
+            // order the runs by tile (== by row) on the host so that a tile range owns a contiguous run range
+            const size_t nr = (size_t)s->n_runs;
+            std::vector<int32_t> h_row(nr), h_len(nr);
+            std::vector<int64_t> h_base(nr), h_head(nr);
+            if (e == cudaSuccess) e = cudaMemcpyAsync(h_row.data(), s->run_row, nr * 4, cudaMemcpyDeviceToHost, stream);
+            if (e == cudaSuccess) e = cudaMemcpyAsync(h_len.data(), s->run_len, nr * 4, cudaMemcpyDeviceToHost, stream);
+            if (e == cudaSuccess) e = cudaMemcpyAsync(h_base.data(), s->run_base, nr * 8, cudaMemcpyDeviceToHost, stream);
+            if (e == cudaSuccess) e = cudaMemcpyAsync(h_head.data(), run_head, nr * 8, cudaMemcpyDeviceToHost, stream);
+            if (e == cudaSuccess) e = cudaStreamSynchronize(stream);
+            cudaFree(run_head);
+            SGL_CUDA_CHECK(e);
+            std::vector<size_t> order(nr);
+            for (size_t i = 0; i < nr; ++i) order[i] = i;
+            std::sort(order.begin(), order.end(), [&](size_t a, size_t b) { return h_head[a] < h_head[b]; });
+            std::vector<int32_t> s_row(nr), s_len(nr);
+            std::vector<int64_t> s_base(nr);
+            s->run_last_tile.resize(nr);
+            for (size_t i = 0; i < nr; ++i) {
+                const size_t o = order[i];
+                s_row[i] = h_row[o];
+                s_len[i] = h_len[o];
+                s_base[i] = h_base[o];
+                s->run_last_tile[i] = h_head[o] + h_len[o];  // the tile after the last carrier finishes the row
+            }
+            SGL_CUDA_CHECK(cudaMemcpyAsync(s->run_row, s_row.data(), nr * 4, cudaMemcpyHostToDevice, stream));
+            SGL_CUDA_CHECK(cudaMemcpyAsync(s->run_len, s_len.data(), nr * 4, cudaMemcpyHostToDevice, stream));
+            SGL_CUDA_CHECK(cudaMemcpyAsync(s->run_base, s_base.data(), nr * 8, cudaMemcpyHostToDevice, stream));
+            SGL_CUDA_CHECK(cudaStreamSynchronize(stream));
         }
         SGL_CUDA_CHECK(cudaStreamSynchronize(stream));
         cudaFree(counts);
@@ -401,6 +434,29 @@ int sglb200_graph_info(sglb200_graph_t g, int64_t info[9])
     info[6] = g->tile_items;
     info[7] = g->split_threshold;
     info[8] = (int64_t)g->bytes_resident;
+    return SGLB200_OK;
+}
+
+int sglb200_graph_chunks(sglb200_graph_t g, int mode, int n_chunks, int64_t *tile_bounds, int64_t *row_bounds)
+{
+    clear_error();
+    SGL_REQUIRE(g && tile_bounds && row_bounds && n_chunks >= 1, "graph_chunks: bad argument");
+    Schedule *s = &g->fast;
+    if (mode == SGLB200_MODE_EXACT) {
+        if (!g->exact.built) {
+            const int st = build_schedule(g, &g->exact, -1, nullptr);
+            if (st != SGLB200_OK) return st;
+        }
+        s = &g->exact;
+    }
+    for (int c = 0; c <= n_chunks; ++c) {
+        tile_bounds[c] = s->n_tiles * (int64_t)c / n_chunks;
+        int32_t row = (int32_t)g->n_rows;
+        if (c < n_chunks && s->n_tiles > 0)
+            SGL_CUDA_CHECK(cudaMemcpy(&row, s->tile_row + tile_bounds[c], sizeof(int32_t), cudaMemcpyDeviceToHost));
+        row_bounds[c] = c == 0 ? 0 : row;
+    }
+    row_bounds[n_chunks] = g->n_rows;
     return SGLB200_OK;
 }
 

@@ -19,6 +19,8 @@
 #include <limits.h>
 #include <stdlib.h>
 
+#include <algorithm>
+
 #include "common.cuh"
 
 namespace sglb200 {
@@ -33,7 +35,8 @@ struct SpmmParams {
     const int32_t *tile_row;
     const int64_t *tile_nnz;
     const int32_t *carry_slot;
-    int64_t n_tiles;
+    int64_t tile_begin;  // first tile of this launch
+    int64_t n_tiles;     // one past the last tile of this launch
     int64_t n_rows;
     const float *X;
     int64_t ldx;
@@ -152,7 +155,7 @@ __global__ void __launch_bounds__(kWarpsPerBlock * 32, MINB) spmm_flat_kernel(co
     // (row to gather, weight) pairs
     __shared__ int2 s_pairs[kWarpsPerBlock][64];
     const int lane = threadIdx.x & 31;
-    const int64_t t = (int64_t)blockIdx.x * kWarpsPerBlock + (threadIdx.x >> 5);
+    const int64_t t = p.tile_begin + (int64_t)blockIdx.x * kWarpsPerBlock + (threadIdx.x >> 5);
     if (t >= p.n_tiles) return;
     int2 *pairs = &s_pairs[threadIdx.x >> 5][0];
 
@@ -348,7 +351,7 @@ __global__ void __launch_bounds__(kWarpsPerBlock * 32, 3) spmm_ring_kernel(const
     extern __shared__ __align__(16) unsigned char smem_raw[];
     const int lane = threadIdx.x & 31;
     const int wib = threadIdx.x >> 5;
-    const int64_t t = (int64_t)blockIdx.x * kWarpsPerBlock + wib;
+    const int64_t t = p.tile_begin + (int64_t)blockIdx.x * kWarpsPerBlock + wib;
     float *ring = reinterpret_cast<float *>(smem_raw) + (size_t)wib * RING * row_floats;
     int2 *pairs = reinterpret_cast<int2 *>(reinterpret_cast<float *>(smem_raw) + (size_t)kWarpsPerBlock * RING * row_floats) + wib * 64;
     if (t >= p.n_tiles) return;
@@ -593,8 +596,19 @@ static void pick_shape(int d, int max_vec, int *vec_out, int *vpl_out, int *col_
     *col_blocks = (d + per_block - 1) / per_block;
 }
 
+int spmm_launch_tiles(sglb200_graph *g, const float *X, int64_t ldx, float *Y, int64_t ldy, int d, int mode,
+                      int accumulate, int64_t tile_begin, int64_t tile_end, cudaStream_t stream);
+
 int spmm_launch(sglb200_graph *g, const float *X, int64_t ldx, float *Y, int64_t ldy, int d, int mode, int accumulate,
                 cudaStream_t stream)
+{
+    return spmm_launch_tiles(g, X, ldx, Y, ldy, d, mode, accumulate, 0, -1, stream);
+}
+
+// launches the hop on the tiles [tile_begin, tile_end) of the schedule (tile_end < 0: all) and folds the cut rows that
+// FINISH inside that range; rows tile_row[tile_begin] .. tile_row[tile_end]-1 of Y are final afterwards
+int spmm_launch_tiles(sglb200_graph *g, const float *X, int64_t ldx, float *Y, int64_t ldy, int d, int mode,
+                      int accumulate, int64_t tile_begin, int64_t tile_end, cudaStream_t stream)
 {
     SGL_REQUIRE(g != nullptr, "spmm: graph is NULL");
     SGL_REQUIRE(d >= 0, "spmm: negative feature width");
@@ -614,6 +628,9 @@ int spmm_launch(sglb200_graph *g, const float *X, int64_t ldx, float *Y, int64_t
         s = &g->exact;
     }
     if (s->n_tiles == 0) return SGLB200_OK;
+    if (tile_end < 0 || tile_end > s->n_tiles) tile_end = s->n_tiles;
+    if (tile_begin < 0) tile_begin = 0;
+    if (tile_begin >= tile_end) return SGLB200_OK;
 
     int max_vec = 4;
     if (d % 4 || ldx % 4 || ldy % 4 || !aligned(X, 16) || !aligned(Y, 16)) max_vec = 2;
@@ -633,7 +650,8 @@ int spmm_launch(sglb200_graph *g, const float *X, int64_t ldx, float *Y, int64_t
     p.tile_row = s->tile_row;
     p.tile_nnz = s->tile_nnz;
     p.carry_slot = s->carry_slot;
-    p.n_tiles = s->n_tiles;
+    p.tile_begin = tile_begin;
+    p.n_tiles = tile_end;
     p.n_rows = g->n_rows;
     p.X = X;
     p.ldx = ldx;
@@ -652,7 +670,7 @@ int spmm_launch(sglb200_graph *g, const float *X, int64_t ldx, float *Y, int64_t
         p.stream_y = force >= 0 ? force : 1;
     }
 
-    const dim3 grid((unsigned)((s->n_tiles + kWarpsPerBlock - 1) / kWarpsPerBlock), (unsigned)col_blocks, 1);
+    const dim3 grid((unsigned)((tile_end - tile_begin + kWarpsPerBlock - 1) / kWarpsPerBlock), (unsigned)col_blocks, 1);
     const bool acc = accumulate != 0;
     cudaError_t e = cudaSuccess;
 #define SGL_SHAPE(V, L, UU, MB) \
@@ -713,17 +731,24 @@ int spmm_launch(sglb200_graph *g, const float *X, int64_t ldx, float *Y, int64_t
 #undef SGL_SHAPE
     SGL_CUDA_CHECK(e);
     if (s->n_runs > 0) {
-        const unsigned blocks = (unsigned)((s->n_runs + kWarpsPerBlock - 1) / kWarpsPerBlock);
-        if (vec == 4)
-            spmm_carry_fixup_kernel<4><<<blocks, kWarpsPerBlock * 32, 0, stream>>>(
-                s->run_row, s->run_base, s->run_len, s->n_runs, g->carry_ws, ws_ld, Y, ldy, d);
-        else if (vec == 2)
-            spmm_carry_fixup_kernel<2><<<blocks, kWarpsPerBlock * 32, 0, stream>>>(
-                s->run_row, s->run_base, s->run_len, s->n_runs, g->carry_ws, ws_ld, Y, ldy, d);
-        else
-            spmm_carry_fixup_kernel<1><<<blocks, kWarpsPerBlock * 32, 0, stream>>>(
-                s->run_row, s->run_base, s->run_len, s->n_runs, g->carry_ws, ws_ld, Y, ldy, d);
-        SGL_CUDA_CHECK(cudaGetLastError());
+        // runs are sorted by tile: those whose finishing tile lies in [tile_begin, tile_end) form one contiguous range
+        const auto &last = s->run_last_tile;
+        const int64_t r0 = std::lower_bound(last.begin(), last.end(), tile_begin) - last.begin();
+        const int64_t r1 = std::lower_bound(last.begin(), last.end(), tile_end) - last.begin();
+        const int64_t nr = r1 - r0;
+        if (nr > 0) {
+            const unsigned blocks = (unsigned)((nr + kWarpsPerBlock - 1) / kWarpsPerBlock);
+            if (vec == 4)
+                spmm_carry_fixup_kernel<4><<<blocks, kWarpsPerBlock * 32, 0, stream>>>(
+                    s->run_row + r0, s->run_base + r0, s->run_len + r0, nr, g->carry_ws, ws_ld, Y, ldy, d);
+            else if (vec == 2)
+                spmm_carry_fixup_kernel<2><<<blocks, kWarpsPerBlock * 32, 0, stream>>>(
+                    s->run_row + r0, s->run_base + r0, s->run_len + r0, nr, g->carry_ws, ws_ld, Y, ldy, d);
+            else
+                spmm_carry_fixup_kernel<1><<<blocks, kWarpsPerBlock * 32, 0, stream>>>(
+                    s->run_row + r0, s->run_base + r0, s->run_len + r0, nr, g->carry_ws, ws_ld, Y, ldy, d);
+            SGL_CUDA_CHECK(cudaGetLastError());
+        }
     }
     return SGLB200_OK;
 }
@@ -755,6 +780,13 @@ int sglb200_spmm(sglb200_graph_t g, const float *X, int64_t ldx, float *Y, int64
 {
     clear_error();
     return spmm_launch(g, X, ldx, Y, ldy, d, mode, accumulate, (cudaStream_t)stream);
+}
+
+int sglb200_spmm_tiles(sglb200_graph_t g, const float *X, int64_t ldx, float *Y, int64_t ldy, int d, int mode,
+                       int64_t tile_begin, int64_t tile_end, void *stream)
+{
+    clear_error();
+    return spmm_launch_tiles(g, X, ldx, Y, ldy, d, mode, 0, tile_begin, tile_end, (cudaStream_t)stream);
 }
 
 int sglb200_propagate(sglb200_graph_t g, float *const *hops, int64_t ld, int d, int K, int mode, void *stream)

@@ -42,6 +42,26 @@ def partition_rows(indptr: np.ndarray, world: int, row_cost: float = 4.0) -> np.
     return np.maximum.accumulate(bounds)
 
 
+TILE_ITEMS = 256  # tile size the partitioned operators are created with (host and device chunk bounds must agree)
+
+
+def chunk_row_bounds(loc_ptr: np.ndarray, n_chunks: int, tile_items: int = TILE_ITEMS) -> np.ndarray:
+    """Rows finished by each of n_chunks consecutive tile ranges of the merge-path schedule (mirrors
+    sglb200_graph_chunks / build_tiles_kernel: boundary tile t sits at item t*tile_items of the merged
+    row-end + non-zero stream; the rows finished before it are those with indptr[r+1] + r <= t*tile_items - 1)."""
+    loc_ptr = np.asarray(loc_ptr, dtype=np.int64)
+    n = loc_ptr.shape[0] - 1
+    total = n + int(loc_ptr[-1])
+    n_tiles = (total + tile_items - 1) // tile_items if total > 0 else 0
+    key = loc_ptr[1:] + np.arange(n, dtype=np.int64)
+    bounds = np.zeros(n_chunks + 1, dtype=np.int64)
+    for c in range(1, n_chunks):
+        k = min((n_tiles * c // n_chunks) * tile_items, total)
+        bounds[c] = np.searchsorted(key, k - 1, side="right")
+    bounds[n_chunks] = n
+    return bounds
+
+
 @dataclass
 class RankPlan:
     """Everything rank `rank` needs: its rectangular CSR with renumbered columns and its exchange lists."""
@@ -53,8 +73,10 @@ class RankPlan:
     data: np.ndarray              # [nnz_local] float32
     n_ext: int                    # columns of the rectangular operator = rows of the extended feature buffer
     mode: str                     # "halo" | "allgather"
-    send_rows: List[np.ndarray]   # halo: per peer, LOCAL row ids this rank must send to that peer
-    recv_counts: List[int]        # halo: rows received from each peer (in peer order)
+    n_chunks: int                 # halo: the hop and its exchange are pipelined over this many row chunks
+    send_rows: List[List[np.ndarray]]   # halo: [chunk][peer] LOCAL row ids this rank sends (sorted)
+    recv_counts: List[List[int]]        # halo: [chunk][peer] rows received
+    chunk_rows: np.ndarray        # halo: [n_chunks+1] local rows finished by each chunk of this rank's hop
     max_rows: int                 # allgather: padded shard length
 
     @property
@@ -77,10 +99,12 @@ def needed_remote_rows(indptr, indices, bounds, rank) -> List[np.ndarray]:
 
 
 def build_plan(indptr, indices, data, n_cols: int, world: int, rank: int, mode: str = "halo",
-               bounds: Optional[np.ndarray] = None, need_from_all: Optional[List[List[np.ndarray]]] = None) -> RankPlan:
+               bounds: Optional[np.ndarray] = None, need_from_all: Optional[List[List[np.ndarray]]] = None,
+               n_chunks: int = 1) -> RankPlan:
     """Plan of one rank from the FULL CSR (every rank holds or can regenerate it; SGL's preprocess is single-process,
-    models/base_model.py:23).  `need_from_all[p][q]` (rows of q needed by p) may be passed when already known;
-    otherwise send lists are derived from the full matrix so that no handshake is needed."""
+    models/base_model.py:23).  Send lists are derived from the full matrix so that no handshake is needed.
+    Halo layout of the extended buffer: [local rows | chunk 0: peer 0 rows, peer 1 rows, ... | chunk 1: ... ] where
+    chunk c of peer q are the rows q's hop finishes in its c-th tile range -- each (chunk) block is one all-to-all."""
     indptr = np.asarray(indptr, dtype=np.int64)
     if bounds is None:
         bounds = partition_rows(indptr, world)
@@ -93,14 +117,31 @@ def build_plan(indptr, indices, data, n_cols: int, world: int, rank: int, mode: 
         max_rows = int(np.max(np.diff(bounds)))
         owner = _owner_of(cols, bounds)
         new_cols = owner * max_rows + (cols - bounds[owner])
-        return RankPlan(rank, world, bounds, loc_ptr, new_cols.astype(np.int32), vals, world * max_rows, mode, [], [],
-                        max_rows)
+        return RankPlan(rank, world, bounds, loc_ptr, new_cols.astype(np.int32), vals, world * max_rows, mode, 1, [], [],
+                        np.array([0, n_local]), max_rows)
     if mode != "halo":
         raise ValueError("mode must be 'halo' or 'allgather'")
-    need = needed_remote_rows(indptr, indices, bounds, rank) if need_from_all is None else need_from_all[rank]
-    recv_counts = [int(a.size) for a in need]
-    # column renumbering: local -> [0, n_local); remote -> n_local + offset(peer) + position in that peer's list
-    offsets = np.concatenate([[0], np.cumsum(recv_counts)]).astype(np.int64)
+    C = max(1, int(n_chunks))
+    # rows finished per chunk, for every rank (a function of that rank's row pointer only)
+    crb = [chunk_row_bounds(indptr[bounds[q]:bounds[q + 1] + 1] - indptr[bounds[q]], C) for q in range(world)]
+    need_all = need_from_all if need_from_all is not None else \
+        [needed_remote_rows(indptr, indices, bounds, p) for p in range(world)]
+    need = need_all[rank]
+    # receive layout: chunk-major, then peer, then row
+    recv_counts = [[0] * world for _ in range(C)]
+    seg_start = np.zeros((C, world), dtype=np.int64)      # offset (in rows, from n_local) of block (c, q)
+    split = []                                            # per peer: positions of the chunk borders in need[q]
+    for q in range(world):
+        local_ids = need[q] - bounds[q]
+        split.append(np.searchsorted(local_ids, crb[q]))
+    pos = 0
+    for c in range(C):
+        for q in range(world):
+            cnt = int(split[q][c + 1] - split[q][c]) if q != rank else 0
+            recv_counts[c][q] = cnt
+            seg_start[c, q] = pos
+            pos += cnt
+    n_halo = pos
     owner = _owner_of(cols, bounds)
     new_cols = np.empty_like(cols)
     is_local = owner == rank
@@ -109,17 +150,20 @@ def build_plan(indptr, indices, data, n_cols: int, world: int, rank: int, mode: 
         m = owner == q
         if q == rank or not m.any():
             continue
-        new_cols[m] = n_local + offsets[q] + np.searchsorted(need[q], cols[m])
-    # what this rank must SEND to every peer p: the rows of `rank` that p needs (derived from the full matrix)
-    send_rows = []
+        idx = np.searchsorted(need[q], cols[m])                        # position in q's sorted need list
+        chunk = np.searchsorted(split[q], idx, side="right") - 1       # which chunk of q finishes that row
+        new_cols[m] = n_local + seg_start[chunk, q] + (idx - split[q][chunk])
+    # what this rank SENDS: for every peer p, the rows of `rank` that p needs, split by this rank's chunks
+    send_rows = [[np.zeros(0, dtype=np.int64) for _ in range(world)] for _ in range(C)]
     for p in range(world):
         if p == rank:
-            send_rows.append(np.zeros(0, dtype=np.int64))
             continue
-        theirs = needed_remote_rows(indptr, indices, bounds, p)[rank] if need_from_all is None else need_from_all[p][rank]
-        send_rows.append((theirs - lo).astype(np.int64))
-    return RankPlan(rank, world, bounds, loc_ptr, new_cols.astype(np.int32), vals, n_local + int(offsets[-1]), mode,
-                    send_rows, recv_counts, 0)
+        theirs = (need_all[p][rank] - lo).astype(np.int64)
+        cut = np.searchsorted(theirs, crb[rank])
+        for c in range(C):
+            send_rows[c][p] = theirs[cut[c]:cut[c + 1]]
+    return RankPlan(rank, world, bounds, loc_ptr, new_cols.astype(np.int32), vals, n_local + n_halo, mode, C,
+                    send_rows, recv_counts, crb[rank], 0)
 
 
 # ---------------------------------------------------------------------------------------------------------------
@@ -127,33 +171,68 @@ def build_plan(indptr, indices, data, n_cols: int, world: int, rank: int, mode: 
 # ---------------------------------------------------------------------------------------------------------------
 class DistOperator:
     """Row-partitioned A^ on this rank.  `local_hop(x_ext, out)` computes out = A_local @ x_ext; the default is the
-    CUDA kernel through CsrOperator.  CPU/gloo tests inject a checker hop to exercise the exchange logic."""
+    CUDA kernel through CsrOperator.  CPU/gloo tests inject a checker hop to exercise the exchange logic.
+
+    With a chunked halo plan on CUDA the hop is pipelined against its own exchange: the tile ranges of the hop run
+    back to back on the compute stream, and as soon as range c has produced its rows their pack + all-to-all runs on
+    a second stream while range c+1 computes."""
 
     def __init__(self, plan: RankPlan, device: Optional[torch.device] = None, group=None,
                  local_hop: Optional[Callable] = None, mode: str = "fast"):
         self.plan = plan
         self.group = group
         self.mode = mode
+        self._tiles = None
         if local_hop is None:
             from .runtime import CsrOperator, require_cuda
             require_cuda()
             self.device = device or torch.device("cuda", torch.cuda.current_device())
-            self._op = CsrOperator(plan.indptr, plan.indices, plan.data, (plan.n_local, plan.n_ext))
+            self._op = CsrOperator(plan.indptr, plan.indices, plan.data, (plan.n_local, plan.n_ext),
+                                   tile_items=TILE_ITEMS)
             self._hop = lambda x_ext, out: self._op.spmm(x_ext, out=out, mode=self.mode)
+            if plan.mode == "halo" and plan.n_chunks > 1 and plan.world > 1:
+                tiles, rows = self._op.chunks(plan.n_chunks, self.mode)
+                if list(rows) != [int(v) for v in plan.chunk_rows]:
+                    raise RuntimeError(f"chunk row bounds differ between host plan {plan.chunk_rows} and device {rows}")
+                self._tiles = tiles
+                self._xstream = torch.cuda.Stream(device=self.device)
         else:
             self.device = device or torch.device("cpu")
             self._op = None
             self._hop = local_hop
-        self._send_idx = [torch.from_numpy(r).to(self.device) for r in plan.send_rows]
-        self._send_all = torch.cat(self._send_idx) if self._send_idx else None
-        self._send_counts = [int(r.size) for r in plan.send_rows]
+        C = plan.n_chunks if plan.mode == "halo" else 0
+        self._send_idx = [torch.from_numpy(np.concatenate(plan.send_rows[c])).to(self.device) if plan.world > 1 else None
+                          for c in range(C)]
+        self._send_counts = [[int(r.size) for r in plan.send_rows[c]] for c in range(C)]
+        self._recv_start = []
+        pos = plan.n_local
+        for c in range(C):
+            self._recv_start.append(pos)
+            pos += int(sum(plan.recv_counts[c]))
         self._bufs = {}
 
     # -- exchange ----------------------------------------------------------------------------------------------
+    def _exchange_chunk(self, ext: torch.Tensor, c: int) -> None:
+        """Send the rows of chunk c every peer needs and receive the peers' chunk-c rows into ext's halo block c."""
+        p = self.plan
+        local = ext[:p.n_local]
+        idx = self._send_idx[c]
+        if idx.numel():
+            if local.is_cuda:
+                from .runtime import gather_rows
+                send = gather_rows([local], idx)[0]               # pack kernel (sglb200_gather_rows)
+            else:
+                send = local[idx]
+        else:
+            send = local.new_zeros((0, ext.shape[1]))
+        n_recv = int(sum(p.recv_counts[c]))
+        recv = ext[self._recv_start[c]:self._recv_start[c] + n_recv]
+        dist.all_to_all_single(recv, send, output_split_sizes=p.recv_counts[c], input_split_sizes=self._send_counts[c],
+                               group=self.group)
+
     def _exchange(self, ext: torch.Tensor) -> None:
         """Fill the remote part of the extended buffer `ext` ([n_ext, d]); the local shard is already in place."""
         p = self.plan
-        n_local, d = p.n_local, ext.shape[1]
         if p.world == 1:
             return
         if p.mode == "allgather":
@@ -161,18 +240,8 @@ class DistOperator:
             mine = ext[p.rank * p.max_rows:(p.rank + 1) * p.max_rows]
             dist.all_gather_into_tensor(ext, mine if mine.is_cuda else mine.clone(), group=self.group)
             return
-        local = ext[:n_local]
-        if self._send_all.numel():
-            if local.is_cuda:
-                from .runtime import gather_rows
-                send = gather_rows([local], self._send_all)[0]      # pack kernel (sglb200_gather_rows)
-            else:
-                send = local[self._send_all]
-        else:
-            send = local.new_zeros((0, d))
-        recv = ext[n_local:]
-        dist.all_to_all_single(recv, send, output_split_sizes=p.recv_counts, input_split_sizes=self._send_counts,
-                               group=self.group)
+        for c in range(p.n_chunks):
+            self._exchange_chunk(ext, c)
 
     def _local_view(self, ext: torch.Tensor) -> torch.Tensor:
         p = self.plan
@@ -189,13 +258,38 @@ class DistOperator:
         bufs = self._bufs[d]
         self._local_view(bufs[0]).copy_(x_local)
         outs = [x_local]
+        if self._tiles is None:
+            for k in range(1, prop_steps + 1):
+                src, dst = bufs[(k - 1) % 2], bufs[k % 2]
+                self._exchange(src)
+                y = self._local_view(dst)
+                self._hop(src, y)
+                if keep == "all" or k == prop_steps:
+                    outs.append(y.clone())
+            return outs
+        # pipelined: the exchange of hop k's rows runs chunk by chunk behind the hop itself
+        cs, xs = torch.cuda.current_stream(), self._xstream
+        xs.wait_stream(cs)
+        with torch.cuda.stream(xs):
+            self._exchange(bufs[0])
+        arrived = xs.record_event()
         for k in range(1, prop_steps + 1):
             src, dst = bufs[(k - 1) % 2], bufs[k % 2]
-            self._exchange(src)
-            y = self._local_view(dst)
-            self._hop(src, y)
-            if keep == "all" or k == prop_steps:
+            cs.wait_event(arrived)                      # every halo row of src is in place
+            y = dst[:p.n_local]
+            last = k == prop_steps
+            for c in range(p.n_chunks):
+                self._op.spmm_tiles(src, y, self._tiles[c], self._tiles[c + 1], mode=self.mode)
+                if not last:
+                    done = cs.record_event()
+                    with torch.cuda.stream(xs):
+                        xs.wait_event(done)
+                        self._exchange_chunk(dst, c)
+            if not last:
+                arrived = xs.record_event()
+            if keep == "all" or last:
                 outs.append(y.clone())
+        cs.wait_stream(xs)
         return outs
 
     def close(self):
@@ -207,4 +301,4 @@ def exchange_volume_bytes(plan: RankPlan, d: int) -> int:
     """Bytes this rank RECEIVES per hop."""
     if plan.mode == "allgather":
         return (plan.world - 1) * plan.max_rows * d * 4
-    return int(sum(plan.recv_counts)) * d * 4
+    return int(sum(sum(c) for c in plan.recv_counts)) * d * 4

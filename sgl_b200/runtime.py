@@ -159,6 +159,22 @@ class CsrOperator:
                                        _MODES[mode], int(accumulate), _stream_ptr()), "spmm")
         return out
 
+    def chunks(self, n_chunks: int, mode="fast"):
+        """(tile_bounds, row_bounds) of n_chunks consecutive tile ranges of the schedule (sglb200_graph_chunks)."""
+        tb = (c_int64 * (n_chunks + 1))()
+        rb = (c_int64 * (n_chunks + 1))()
+        check(_lib.load().sglb200_graph_chunks(self._h, _MODES[mode], int(n_chunks), tb, rb), "graph_chunks")
+        return [int(v) for v in tb], [int(v) for v in rb]
+
+    def spmm_tiles(self, x: torch.Tensor, out: torch.Tensor, tile_begin: int, tile_end: int, mode="fast"):
+        """The hop restricted to the tiles [tile_begin, tile_end): fills the rows that range finishes."""
+        d = int(x.shape[1])
+        ldx = int(x.stride(0)) if x.shape[0] > 1 else d
+        ldy = int(out.stride(0)) if out.shape[0] > 1 else d
+        check(_lib.load().sglb200_spmm_tiles(self._h, c_void_p(x.data_ptr()), ldx, c_void_p(out.data_ptr()), ldy, d,
+                                             _MODES[mode], int(tile_begin), int(tile_end), _stream_ptr()), "spmm_tiles")
+        return out
+
     # ---- K hops, device resident ------------------------------------------------------------------------------
     def propagate(self, x: torch.Tensor, prop_steps: int, mode="fast", concat: bool = False) -> List[torch.Tensor]:
         """[x, A x, ..., A^K x] as CUDA tensors.  concat=True lays the K+1 slabs out as column blocks of one

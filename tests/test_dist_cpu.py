@@ -11,7 +11,7 @@ import torch.distributed as dist
 import torch.multiprocessing as mp
 
 from oracle import sgap_oracle as O
-from sgl_b200.dist import DistOperator, build_plan, exchange_volume_bytes, partition_rows
+from sgl_b200.dist import DistOperator, build_plan, chunk_row_bounds, exchange_volume_bytes, partition_rows
 
 
 def _graph(seed=0, n=600, m=5000):
@@ -38,19 +38,24 @@ def test_plans_renumber_columns_consistently():
     x = np.random.default_rng(2).standard_normal((a.shape[0], 8)).astype(np.float32)
     ref = O.spmm_hop(a, x, "fma")
     bounds = partition_rows(a.indptr, world)
-    for mode in ("halo", "allgather"):
-        plans = [build_plan(a.indptr, a.indices, a.data, a.shape[1], world, r, mode) for r in range(world)]
+    for mode, chunks in (("halo", 1), ("halo", 3), ("allgather", 1)):
+        plans = [build_plan(a.indptr, a.indices, a.data, a.shape[1], world, r, mode, n_chunks=chunks)
+                 for r in range(world)]
         for p in plans:
             lo, hi = bounds[p.rank], bounds[p.rank + 1]
             ext = np.zeros((p.n_ext, 8), dtype=np.float32)
             if mode == "halo":
                 ext[:p.n_local] = x[lo:hi]
                 pos = p.n_local
-                for q in range(world):      # what the all-to-all would deliver: rows q sends to p, in q's send order
-                    rows_q = plans[q].send_rows[p.rank] + bounds[q]
-                    assert len(rows_q) == p.recv_counts[q]
-                    ext[pos:pos + len(rows_q)] = x[rows_q]
-                    pos += len(rows_q)
+                for c in range(chunks):     # what all-to-all c would deliver: rows q sends to p, in q's send order
+                    for q in range(world):
+                        rows_q = plans[q].send_rows[c][p.rank] + bounds[q]
+                        assert len(rows_q) == p.recv_counts[c][q]
+                        # rows of chunk c are exactly those q's hop finishes in its c-th tile range
+                        assert np.all((rows_q - bounds[q] >= plans[q].chunk_rows[c]) &
+                                      (rows_q - bounds[q] < plans[q].chunk_rows[c + 1]))
+                        ext[pos:pos + len(rows_q)] = x[rows_q]
+                        pos += len(rows_q)
                 assert pos == p.n_ext
             else:
                 for q in range(world):
@@ -71,14 +76,14 @@ def _free_port():
     return port
 
 
-def _worker(rank, world, port, mode, K, d, out_dir):
+def _worker(rank, world, port, mode, K, d, out_dir, chunks=1):
     os.environ["MASTER_ADDR"] = "127.0.0.1"
     os.environ["MASTER_PORT"] = str(port)
     dist.init_process_group("gloo", rank=rank, world_size=world)
     try:
         a = _graph(3)
         x = np.random.default_rng(4).standard_normal((a.shape[0], d)).astype(np.float32)
-        plan = build_plan(a.indptr, a.indices, a.data, a.shape[1], world, rank, mode)
+        plan = build_plan(a.indptr, a.indices, a.data, a.shape[1], world, rank, mode, n_chunks=chunks)
 
         def oracle_hop(x_ext, out):          # checker kernel standing in for sglb200_spmm on the CPU
             y = np.zeros((plan.n_local, d), dtype=np.float32)
@@ -95,11 +100,11 @@ def _worker(rank, world, port, mode, K, d, out_dir):
 
 
 @pytest.mark.parametrize("world", [2, 3])
-@pytest.mark.parametrize("mode", ["halo", "allgather"])
-def test_distributed_propagate_matches_single_process(tmp_path, world, mode):
+@pytest.mark.parametrize("mode,chunks", [("halo", 1), ("halo", 4), ("allgather", 1)])
+def test_distributed_propagate_matches_single_process(tmp_path, world, mode, chunks):
     K, d = 3, 12
     port = _free_port()
-    mp.spawn(_worker, args=(world, port, mode, K, d, str(tmp_path)), nprocs=world, join=True)
+    mp.spawn(_worker, args=(world, port, mode, K, d, str(tmp_path), chunks), nprocs=world, join=True)
     a = _graph(3)
     x = np.random.default_rng(4).standard_normal((a.shape[0], d)).astype(np.float32)
     ref = np.stack(O.propagate(a, x, K, "fma"))

@@ -11,7 +11,7 @@ from oracle import sgap_oracle as O
 pytestmark = pytest.mark.gpu
 
 
-def _worker(rank, world, port, mode, tmp):
+def _worker(rank, world, port, mode, tmp, chunks=1):
     import scipy.sparse as sp
     import torch.distributed as dist
     from sgl_b200.dist import DistOperator, build_plan
@@ -27,7 +27,7 @@ def _worker(rank, world, port, mode, tmp):
                              (np.concatenate([rows, cols]), np.concatenate([cols, rows]))), shape=(n, n))
         a = O.laplacian_adj(adj, 0.5)
         x = rng.standard_normal((n, d)).astype(np.float32)
-        plan = build_plan(a.indptr, a.indices, a.data, n, world, rank, mode)
+        plan = build_plan(a.indptr, a.indices, a.data, n, world, rank, mode, n_chunks=chunks)
         op = DistOperator(plan, mode="exact")
         lo, hi = plan.bounds[rank], plan.bounds[rank + 1]
         hops = op.propagate(torch.from_numpy(x[lo:hi]).cuda(), K)
@@ -39,8 +39,8 @@ def _worker(rank, world, port, mode, tmp):
         dist.destroy_process_group()
 
 
-@pytest.mark.parametrize("mode", ["halo", "allgather"])
-def test_two_rank_nccl_row_partition(tmp_path, mode):
+@pytest.mark.parametrize("mode,chunks", [("halo", 1), ("halo", 4), ("allgather", 1)])
+def test_two_rank_nccl_row_partition(tmp_path, mode, chunks):
     if not torch.cuda.is_available() or torch.cuda.device_count() < 2:
         pytest.skip("needs 2 GPUs")
     import torch.multiprocessing as mp
@@ -48,7 +48,7 @@ def test_two_rank_nccl_row_partition(tmp_path, mode):
     s.bind(("127.0.0.1", 0))
     port = s.getsockname()[1]
     s.close()
-    mp.spawn(_worker, args=(2, port, mode, str(tmp_path)), nprocs=2, join=True)
+    mp.spawn(_worker, args=(2, port, mode, str(tmp_path), chunks), nprocs=2, join=True)
     ref, bounds = np.load(tmp_path / "ref.npy"), np.load(tmp_path / "bounds.npy")
     for r in range(2):
         got = np.load(tmp_path / f"{mode}_{r}.npy")

@@ -514,3 +514,27 @@ def test_fused_learnable_larger_batch_matches_torch_expressions():
         assert torch.allclose(outs[0], outs[1], rtol=1e-5, atol=1e-6), kind
         for a, b in zip(grads[0], grads[1]):
             assert torch.allclose(a, b, rtol=2e-4, atol=1e-7), kind
+
+
+def test_tile_ranges_compose_to_the_full_hop():
+    """sglb200_spmm_tiles over consecutive chunks == sglb200_spmm, bit for bit (same tiles, same folds), and the device
+    chunk bounds equal the host formula the row partitioner uses."""
+    from sgl_b200.dist import chunk_row_bounds
+    rng = np.random.default_rng(43)
+    n, d = 6000, 128
+    a = O.laplacian_adj(random_graph(rng, n, 90000, skew=1.15), 0.5)
+    op = CsrOperator(a.indptr, a.indices, a.data.astype(np.float32), a.shape, tile_items=256)
+    assert op.info()["carry_runs"] > 0
+    x = torch.from_numpy(rng.standard_normal((n, d)).astype(np.float32)).cuda()
+    full = op.spmm(x, mode="fast")
+    for n_chunks in (1, 3, 7):
+        tiles, rows = op.chunks(n_chunks, "fast")
+        assert rows == [int(v) for v in chunk_row_bounds(a.indptr, n_chunks, 256)]
+        out = torch.full_like(full, float("nan"))
+        for c in range(n_chunks):
+            op.spmm_tiles(x, out, tiles[c], tiles[c + 1], mode="fast")
+            torch.cuda.synchronize()
+            done = out[:rows[c + 1]]
+            assert torch.equal(done, full[:rows[c + 1]])       # rows finished so far are final
+        assert torch.equal(out, full)
+    op.close()
