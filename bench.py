@@ -54,6 +54,8 @@ def parse_args():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--exchange", default="halo", choices=["halo", "allgather"])
+    ap.add_argument("--transport", default="peer", choices=["peer", "nccl"],
+                    help="halo rows move by our NVLink peer-store kernels (CUDA IPC) or by NCCL all_to_all")
     ap.add_argument("--chunks", type=int, default=4, help="row chunks the hop is pipelined over against its halo exchange")
     return ap.parse_args()
 
@@ -417,6 +419,7 @@ def run_dist(args):
     from sgl_b200.graph_build import normalized_adjacency_device, values_from_parts
 
     rank, world = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"])
+    os.environ["SGLB200_DIST_TRANSPORT"] = args.transport
     local = int(os.environ.get("LOCAL_RANK", rank))
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
@@ -485,6 +488,7 @@ def run_dist(args):
                 "warmup": max(args.warmup, 3), "ms_per_step": 1e3 * total_s / args.steps, "higher_is_better": True,
                 "scaling": "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
                 "config": dict(workload_config(name, n, nnz, d, K, args), exchange=args.exchange, chunks=args.chunks,
+                               transport=op.transport,
                                halo_recv_bytes_per_hop_max_rank=float(recv.item())),
                 "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak * world, "unit": "GB/s",
                              "frac": achieved / (peak * world), "traffic": None, "kernel": "spmm_flat_kernel",

@@ -157,6 +157,22 @@ SGLB200_API int sglb200_lw_backward(int kind, const float *const *feats, int n_a
 SGLB200_API int sglb200_gather_rows(const float *const *feats, int n_feats, int64_t ld_in, const int64_t *idx, int64_t B, int d,
                         float *const *outs, int64_t ld_out, void *stream);
 
+/* ---- (e) halo exchange over NVLink peer memory (row partition, one process per GPU) ---------------------------
+ * The reference has no collective on this path; these are the primitives of sgl_b200/dist.py's
+ * NCCL-free exchange.  ipc_alloc: cudaMalloc + zero + CUDA IPC handle (64 bytes) that the other ranks of the box open
+ * with ipc_open (peer access enabled lazily).  push_rows: dst[i, :] = src[rows[i], :] for i < n_rows with dst in a
+ * PEER's memory (128-bit stores over NVLink); rows is a device array.  signal_peers: after everything previously
+ * enqueued on `stream`, store `value` (release, system scope) to the n flag words whose (peer) addresses are listed
+ * in the device array flag_ptrs_dev.  wait_flags: hold `stream` until the n local flag words are all >= value. */
+SGLB200_API int sglb200_ipc_alloc(int64_t bytes, void **ptr, unsigned char handle[64]);
+SGLB200_API int sglb200_ipc_open(const unsigned char handle[64], void **ptr);
+SGLB200_API int sglb200_ipc_close(void *ptr);
+SGLB200_API int sglb200_ipc_free(void *ptr);
+SGLB200_API int sglb200_push_rows(const float *src, int64_t ld_src, int d, const int64_t *rows, int64_t n_rows, float *dst,
+                      int64_t ld_dst, int max_blocks, void *stream);
+SGLB200_API int sglb200_signal_peers(unsigned long long *const *flag_ptrs_dev, int n, unsigned long long value, void *stream);
+SGLB200_API int sglb200_wait_flags(const unsigned long long *flags_dev, int n, unsigned long long value, void *stream);
+
 /* ---- legacy ABI: drop-in for the reference's two shared objects ----------------------------------------------
  * Same symbols, same signatures, host pointers, `answer` is accumulated into (matmul.c:36-37).  Internally:
  * upload -> EXACT-mode kernel -> download.  int32 offsets as in the reference, but N*d may exceed 2^31. */

@@ -45,6 +45,13 @@ SIGNATURES = {
                                     c_void_p]),
     "sglb200_gather_rows": (c_int, [POINTER(c_void_p), c_int, c_int64, c_void_p, c_int64, c_int, POINTER(c_void_p),
                                     c_int64, c_void_p]),
+    "sglb200_ipc_alloc": (c_int, [c_int64, POINTER(c_void_p), c_void_p]),
+    "sglb200_ipc_open": (c_int, [c_void_p, POINTER(c_void_p)]),
+    "sglb200_ipc_close": (c_int, [c_void_p]),
+    "sglb200_ipc_free": (c_int, [c_void_p]),
+    "sglb200_push_rows": (c_int, [c_void_p, c_int64, c_int, c_void_p, c_int64, c_void_p, c_int64, c_int, c_void_p]),
+    "sglb200_signal_peers": (c_int, [c_void_p, c_int, ctypes.c_uint64, c_void_p]),
+    "sglb200_wait_flags": (c_int, [c_void_p, c_int, ctypes.c_uint64, c_void_p]),
     "FloatCSRMulDenseOMP": (None, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int]),
     "FloatCSRMulDense": (c_int, [c_void_p, c_int, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int]),
 }

@@ -20,6 +20,7 @@ the gloo backend (tests/test_dist_cpu.py).
 """
 from __future__ import annotations
 
+import os
 from dataclasses import dataclass
 from typing import Callable, List, Optional
 
@@ -167,6 +168,76 @@ def build_plan(indptr, indices, data, n_cols: int, world: int, rank: int, mode: 
 
 
 # ---------------------------------------------------------------------------------------------------------------
+# NVLink peer memory (CUDA IPC) for the NCCL-free halo exchange
+# ---------------------------------------------------------------------------------------------------------------
+class _RawCuda:
+    """Exposes a raw device allocation to torch through the CUDA array interface (no ownership)."""
+
+    def __init__(self, ptr, shape, typestr):
+        self.__cuda_array_interface__ = {"shape": tuple(shape), "typestr": typestr, "data": (int(ptr), False),
+                                         "version": 3, "strides": None}
+
+
+class PeerSlabs:
+    """Two extended feature slabs + one flag word per rank, allocated with sglb200_ipc_alloc and mapped by every other
+    rank of the box.  Collective constructor (all ranks of `group`)."""
+
+    FLAG_BYTES = 4096
+
+    def __init__(self, n_ext: int, d: int, device, group=None):
+        import ctypes
+        from . import _lib
+        self._lib = _lib.load()
+        self.world = dist.get_world_size(group)
+        self.rank = dist.get_rank(group)
+        self.n_ext, self.d = int(n_ext), int(d)
+        slab_bytes = ((self.n_ext * self.d * 4 + 255) // 256) * 256
+        self.slab_bytes = slab_bytes
+        total = self.FLAG_BYTES + 2 * slab_bytes
+        ptr = ctypes.c_void_p()
+        handle = (ctypes.c_ubyte * 64)()
+        with torch.cuda.device(device):
+            _lib.check(self._lib.sglb200_ipc_alloc(total, ctypes.byref(ptr), handle), "ipc_alloc")
+        self.base = int(ptr.value)
+        gathered = [None] * self.world
+        dist.all_gather_object(gathered, (bytes(handle), slab_bytes), group=group)
+        self.peer_base, self.peer_slab_bytes = [], []
+        for q, (h, sb) in enumerate(gathered):
+            if q == self.rank:
+                self.peer_base.append(self.base)
+            else:
+                p = ctypes.c_void_p()
+                buf = (ctypes.c_ubyte * 64).from_buffer_copy(h)
+                with torch.cuda.device(device):
+                    _lib.check(self._lib.sglb200_ipc_open(buf, ctypes.byref(p)), "ipc_open")
+                self.peer_base.append(int(p.value))
+            self.peer_slab_bytes.append(int(sb))
+        self.slabs = [torch.as_tensor(_RawCuda(self.base + self.FLAG_BYTES + i * slab_bytes, (self.n_ext, self.d), "<f4"),
+                                      device=device) for i in range(2)]
+        self.flags = torch.as_tensor(_RawCuda(self.base, (self.world,), "<i8"), device=device)
+        # device array of the addresses of MY flag word inside every rank's flag block
+        self.flag_ptrs = torch.tensor([b + 8 * self.rank for b in self.peer_base], dtype=torch.int64, device=device)
+        dist.barrier(group=group)
+
+    def peer_slab_ptr(self, q: int, which: int, row: int) -> int:
+        return self.peer_base[q] + self.FLAG_BYTES + which * self.peer_slab_bytes[q] + row * self.d * 4
+
+    def close(self):
+        for q, b in enumerate(self.peer_base):
+            if q != self.rank and b:
+                self._lib.sglb200_ipc_close(ctypes_void(b))
+        if self.base:
+            self._lib.sglb200_ipc_free(ctypes_void(self.base))
+        self.base = 0
+        self.peer_base = []
+
+
+def ctypes_void(v):
+    import ctypes
+    return ctypes.c_void_p(int(v))
+
+
+# ---------------------------------------------------------------------------------------------------------------
 # distributed operator
 # ---------------------------------------------------------------------------------------------------------------
 class DistOperator:
@@ -210,6 +281,99 @@ class DistOperator:
             self._recv_start.append(pos)
             pos += int(sum(plan.recv_counts[c]))
         self._bufs = {}
+        # transport of the halo rows: "peer" = stores into the peers' slabs over NVLink (CUDA IPC, own kernels),
+        # "nccl" = pack + all_to_all_single.  Peer needs CUDA, a halo plan and more than one rank.
+        want = os.environ.get("SGLB200_DIST_TRANSPORT", "peer")
+        self.transport = "peer" if (want == "peer" and local_hop is None and plan.mode == "halo" and plan.world > 1) \
+            else "nccl"
+        self._peer = {}
+        self._epoch = 0
+        if self.transport == "peer":
+            # where MY rows land inside every receiver: receiver q's block (chunk c, sender me) starts at row
+            # recv_pos[q][c][me] of q's extended slab
+            mine = [[self._recv_start[c] + int(sum(plan.recv_counts[c][:q])) for q in range(plan.world)] for c in range(C)]
+            table = [None] * plan.world
+            dist.all_gather_object(table, mine, group=group)
+            self._dst_row = [[table[q][c][plan.rank] for q in range(plan.world)] for c in range(C)]
+            self._send_per_peer = [[torch.from_numpy(plan.send_rows[c][q]).to(self.device) for q in range(plan.world)]
+                                   for c in range(C)]
+            if self._tiles is None:
+                self._xstream = torch.cuda.Stream(device=self.device)
+
+    # -- exchange over peer memory ---------------------------------------------------------------------------------
+    def _peer_slabs(self, d: int) -> PeerSlabs:
+        if d not in self._peer:
+            self._peer[d] = PeerSlabs(self.plan.n_ext, d, self.device, self.group)
+        return self._peer[d]
+
+    def _push_chunk(self, ps: PeerSlabs, which: int, c: int) -> None:
+        """Copy the rows of chunk c that each peer references from my slab `which` into that peer's slab `which`."""
+        from . import _lib
+        lib = _lib.load()
+        p = self.plan
+        src = ps.slabs[which]
+        stream = ctypes_void(torch.cuda.current_stream().cuda_stream)
+        for q in range(p.world):
+            rows = self._send_per_peer[c][q]
+            if q == p.rank or rows.numel() == 0:
+                continue
+            _lib.check(lib.sglb200_push_rows(ctypes_void(src.data_ptr()), ps.d, ps.d, ctypes_void(rows.data_ptr()),
+                                             int(rows.numel()), ctypes_void(ps.peer_slab_ptr(q, which, self._dst_row[c][q])),
+                                             ps.d, 0, stream), "push_rows")
+
+    def _signal(self, ps: PeerSlabs) -> int:
+        """Publish 'everything I enqueued so far on this stream has been written' to every rank; returns the epoch."""
+        from . import _lib
+        self._epoch += 1
+        _lib.check(_lib.load().sglb200_signal_peers(ctypes_void(ps.flag_ptrs.data_ptr()), self.plan.world, self._epoch,
+                                                    ctypes_void(torch.cuda.current_stream().cuda_stream)), "signal_peers")
+        return self._epoch
+
+    def _wait(self, ps: PeerSlabs, epoch: int) -> None:
+        from . import _lib
+        _lib.check(_lib.load().sglb200_wait_flags(ctypes_void(ps.flags.data_ptr()), self.plan.world, epoch,
+                                                  ctypes_void(torch.cuda.current_stream().cuda_stream)), "wait_flags")
+
+    def _propagate_peer(self, x_local: torch.Tensor, prop_steps: int, keep: str) -> List[torch.Tensor]:
+        p = self.plan
+        d = int(x_local.shape[1])
+        ps = self._peer_slabs(d)
+        cs, xs = torch.cuda.current_stream(), self._xstream
+        n_chunks = p.n_chunks
+        tiles = self._tiles
+        # nobody may still be reading the slabs of a previous call when the first rows arrive
+        self._wait(ps, self._signal(ps))
+        ps.slabs[0][:p.n_local].copy_(x_local)
+        for c in range(n_chunks):
+            self._push_chunk(ps, 0, c)
+        arrived = self._signal(ps)
+        outs = [x_local]
+        for k in range(1, prop_steps + 1):
+            src, dst = ps.slabs[(k - 1) % 2], ps.slabs[k % 2]
+            self._wait(ps, arrived)                        # every peer has delivered the halo rows of src
+            y = dst[:p.n_local]
+            last = k == prop_steps
+            if tiles is None:
+                self._op.spmm(src, out=y, mode=self.mode)
+                if not last:
+                    for c in range(n_chunks):
+                        self._push_chunk(ps, k % 2, c)
+                    arrived = self._signal(ps)
+            else:
+                for c in range(n_chunks):
+                    self._op.spmm_tiles(src, y, tiles[c], tiles[c + 1], mode=self.mode)
+                    if not last:
+                        done = cs.record_event()
+                        with torch.cuda.stream(xs):
+                            xs.wait_event(done)
+                            self._push_chunk(ps, k % 2, c)
+                if not last:
+                    with torch.cuda.stream(xs):
+                        arrived = self._signal(ps)          # ordered behind all pushes of this hop
+            if keep == "all" or last:
+                outs.append(y.clone())
+        cs.wait_stream(xs)
+        return outs
 
     # -- exchange ----------------------------------------------------------------------------------------------
     def _exchange_chunk(self, ext: torch.Tensor, c: int) -> None:
@@ -252,6 +416,8 @@ class DistOperator:
     def propagate(self, x_local: torch.Tensor, prop_steps: int, keep: str = "all") -> List[torch.Tensor]:
         """[X_p, (A^X)_p, ..., (A^^K X)_p] for this rank's rows (keep='last': only the last hop is retained)."""
         p = self.plan
+        if self.transport == "peer":
+            return self._propagate_peer(x_local, prop_steps, keep)
         d = int(x_local.shape[1])
         if d not in self._bufs:  # two extended slabs, reused across calls (padding rows stay zero)
             self._bufs[d] = [torch.zeros((p.n_ext, d), dtype=torch.float32, device=self.device) for _ in range(2)]
@@ -268,6 +434,8 @@ class DistOperator:
                     outs.append(y.clone())
             return outs
         # pipelined: the exchange of hop k's rows runs chunk by chunk behind the hop itself
+        trace = os.environ.get("SGLB200_DIST_TRACE") == "1"
+        marks = []
         cs, xs = torch.cuda.current_stream(), self._xstream
         xs.wait_stream(cs)
         with torch.cuda.stream(xs):
@@ -279,20 +447,39 @@ class DistOperator:
             y = dst[:p.n_local]
             last = k == prop_steps
             for c in range(p.n_chunks):
+                if trace:
+                    e0 = torch.cuda.Event(enable_timing=True); e0.record(cs)
                 self._op.spmm_tiles(src, y, self._tiles[c], self._tiles[c + 1], mode=self.mode)
+                if trace:
+                    e1 = torch.cuda.Event(enable_timing=True); e1.record(cs)
+                    marks.append(("hop%d.compute%d" % (k, c), e0, e1))
                 if not last:
                     done = cs.record_event()
                     with torch.cuda.stream(xs):
                         xs.wait_event(done)
+                        if trace:
+                            x0 = torch.cuda.Event(enable_timing=True); x0.record(xs)
                         self._exchange_chunk(dst, c)
+                        if trace:
+                            x1 = torch.cuda.Event(enable_timing=True); x1.record(xs)
+                            marks.append(("hop%d.exchange%d" % (k, c), x0, x1))
             if not last:
                 arrived = xs.record_event()
             if keep == "all" or last:
                 outs.append(y.clone())
         cs.wait_stream(xs)
+        if trace and marks:
+            torch.cuda.synchronize()
+            t0 = marks[0][1]
+            print("[dist trace rank %d] " % p.rank + "  ".join(
+                "%s@%.2f+%.2fms" % (n, t0.elapsed_time(a), a.elapsed_time(b)) for n, a, b in marks[:4 * p.n_chunks]),
+                flush=True)
         return outs
 
     def close(self):
+        for ps in self._peer.values():
+            ps.close()
+        self._peer = {}
         if self._op is not None:
             self._op.close()
 

@@ -1,4 +1,5 @@
-"""GPU test (-m gpu, needs >= 2 devices, skipped otherwise): the row-partitioned operator over NCCL, 2 ranks."""
+"""GPU test (-m gpu, needs >= 2 devices, skipped otherwise): the row-partitioned operator on 2 ranks, halo rows moved
+either by our own NVLink peer-memory kernels (CUDA IPC) or by NCCL."""
 import os
 import socket
 
@@ -11,11 +12,12 @@ from oracle import sgap_oracle as O
 pytestmark = pytest.mark.gpu
 
 
-def _worker(rank, world, port, mode, tmp, chunks=1):
+def _worker(rank, world, port, mode, tmp, chunks=1, transport="peer"):
     import scipy.sparse as sp
     import torch.distributed as dist
     from sgl_b200.dist import DistOperator, build_plan
     os.environ["MASTER_ADDR"], os.environ["MASTER_PORT"] = "127.0.0.1", str(port)
+    os.environ["SGLB200_DIST_TRANSPORT"] = transport
     torch.cuda.set_device(rank)
     dist.init_process_group("nccl", rank=rank, world_size=world, device_id=torch.device("cuda", rank))
     try:
@@ -31,6 +33,9 @@ def _worker(rank, world, port, mode, tmp, chunks=1):
         op = DistOperator(plan, mode="exact")
         lo, hi = plan.bounds[rank], plan.bounds[rank + 1]
         hops = op.propagate(torch.from_numpy(x[lo:hi]).cuda(), K)
+        again = op.propagate(torch.from_numpy(x[lo:hi]).cuda(), K)        # slabs and flags are reused across calls
+        assert all(torch.equal(a, b) for a, b in zip(hops, again))
+        assert op.transport == (transport if mode == "halo" else "nccl")
         np.save(os.path.join(tmp, f"{mode}_{rank}.npy"), np.stack([h.cpu().numpy() for h in hops]))
         if rank == 0:
             np.save(os.path.join(tmp, "ref.npy"), np.stack(O.propagate(a, x, K, "fma")))
@@ -39,8 +44,9 @@ def _worker(rank, world, port, mode, tmp, chunks=1):
         dist.destroy_process_group()
 
 
-@pytest.mark.parametrize("mode,chunks", [("halo", 1), ("halo", 4), ("allgather", 1)])
-def test_two_rank_nccl_row_partition(tmp_path, mode, chunks):
+@pytest.mark.parametrize("mode,chunks,transport", [("halo", 1, "peer"), ("halo", 4, "peer"), ("halo", 1, "nccl"),
+                                                   ("halo", 4, "nccl"), ("allgather", 1, "nccl")])
+def test_two_rank_nccl_row_partition(tmp_path, mode, chunks, transport):
     if not torch.cuda.is_available() or torch.cuda.device_count() < 2:
         pytest.skip("needs 2 GPUs")
     import torch.multiprocessing as mp
@@ -48,7 +54,7 @@ def test_two_rank_nccl_row_partition(tmp_path, mode, chunks):
     s.bind(("127.0.0.1", 0))
     port = s.getsockname()[1]
     s.close()
-    mp.spawn(_worker, args=(2, port, mode, str(tmp_path), chunks), nprocs=2, join=True)
+    mp.spawn(_worker, args=(2, port, mode, str(tmp_path), chunks, transport), nprocs=2, join=True)
     ref, bounds = np.load(tmp_path / "ref.npy"), np.load(tmp_path / "bounds.npy")
     for r in range(2):
         got = np.load(tmp_path / f"{mode}_{r}.npy")
