@@ -266,7 +266,7 @@ class DistOperator:
                 if list(rows) != [int(v) for v in plan.chunk_rows]:
                     raise RuntimeError(f"chunk row bounds differ between host plan {plan.chunk_rows} and device {rows}")
                 self._tiles = tiles
-                self._xstream = torch.cuda.Stream(device=self.device)
+                self._xstream = torch.cuda.Stream(device=self.device, priority=-1)
         else:
             self.device = device or torch.device("cpu")
             self._op = None
@@ -298,7 +298,9 @@ class DistOperator:
             self._send_per_peer = [[torch.from_numpy(plan.send_rows[c][q]).to(self.device) for q in range(plan.world)]
                                    for c in range(C)]
             if self._tiles is None:
-                self._xstream = torch.cuda.Stream(device=self.device)
+                self._xstream = torch.cuda.Stream(device=self.device, priority=-1)
+            # grid cap of pushes that overlap a hop (0 = none: measured best on 2 x B200, profiles/)
+            self._push_blocks = int(os.environ.get("SGLB200_PUSH_BLOCKS", "0"))  # 0 = full grid (measured best)
 
     # -- exchange over peer memory ---------------------------------------------------------------------------------
     def _peer_slabs(self, d: int) -> PeerSlabs:
@@ -306,7 +308,7 @@ class DistOperator:
             self._peer[d] = PeerSlabs(self.plan.n_ext, d, self.device, self.group)
         return self._peer[d]
 
-    def _push_chunk(self, ps: PeerSlabs, which: int, c: int) -> None:
+    def _push_chunk(self, ps: PeerSlabs, which: int, c: int, blocks: int = 0) -> None:
         """Copy the rows of chunk c that each peer references from my slab `which` into that peer's slab `which`."""
         from . import _lib
         lib = _lib.load()
@@ -319,7 +321,7 @@ class DistOperator:
                 continue
             _lib.check(lib.sglb200_push_rows(ctypes_void(src.data_ptr()), ps.d, ps.d, ctypes_void(rows.data_ptr()),
                                              int(rows.numel()), ctypes_void(ps.peer_slab_ptr(q, which, self._dst_row[c][q])),
-                                             ps.d, 0, stream), "push_rows")
+                                             ps.d, blocks, stream), "push_rows")
 
     def _signal(self, ps: PeerSlabs) -> int:
         """Publish 'everything I enqueued so far on this stream has been written' to every rank; returns the epoch."""
@@ -338,6 +340,8 @@ class DistOperator:
         p = self.plan
         d = int(x_local.shape[1])
         ps = self._peer_slabs(d)
+        trace = os.environ.get("SGLB200_DIST_TRACE") == "1"
+        marks = []
         cs, xs = torch.cuda.current_stream(), self._xstream
         n_chunks = p.n_chunks
         tiles = self._tiles
@@ -361,18 +365,34 @@ class DistOperator:
                     arrived = self._signal(ps)
             else:
                 for c in range(n_chunks):
+                    if trace:
+                        e0 = torch.cuda.Event(enable_timing=True); e0.record(cs)
                     self._op.spmm_tiles(src, y, tiles[c], tiles[c + 1], mode=self.mode)
+                    if trace:
+                        e1 = torch.cuda.Event(enable_timing=True); e1.record(cs)
+                        marks.append(("hop%d.compute%d" % (k, c), e0, e1))
                     if not last:
                         done = cs.record_event()
                         with torch.cuda.stream(xs):
                             xs.wait_event(done)
-                            self._push_chunk(ps, k % 2, c)
+                            if trace:
+                                x0 = torch.cuda.Event(enable_timing=True); x0.record(xs)
+                            self._push_chunk(ps, k % 2, c, self._push_blocks if c + 1 < n_chunks else 0)
+                            if trace:
+                                x1 = torch.cuda.Event(enable_timing=True); x1.record(xs)
+                                marks.append(("hop%d.push%d" % (k, c), x0, x1))
                 if not last:
                     with torch.cuda.stream(xs):
                         arrived = self._signal(ps)          # ordered behind all pushes of this hop
             if keep == "all" or last:
                 outs.append(y.clone())
         cs.wait_stream(xs)
+        if trace and marks:
+            torch.cuda.synchronize()
+            t0 = marks[0][1]
+            print("[dist trace rank %d] " % p.rank + "  ".join(
+                "%s@%.2f+%.2fms" % (n, t0.elapsed_time(a), a.elapsed_time(b)) for n, a, b in marks[:4 * n_chunks]),
+                flush=True)
         return outs
 
     # -- exchange ----------------------------------------------------------------------------------------------
