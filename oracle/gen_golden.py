@@ -187,7 +187,25 @@ def gen_message_cases():
     print("wrote message_ops", len(out), "arrays")
 
 
+def gen_trick_cases():
+    """label propagation (sgl/tricks/utils.py:40-58), an adjacent consumer of the same hop."""
+    from sgl.tricks.utils import adj_to_symmetric_norm as tricks_norm, label_propagation
+    adj = graphs()["skewed200"]
+    n = adj.shape[0]
+    gen = torch.Generator().manual_seed(5)
+    labels = torch.randint(0, 6, (n,), generator=gen)
+    mask = torch.rand(n, generator=gen) < 0.4
+    norm = tricks_norm(adj, 0.5)
+    out = {"labels": labels.numpy(), "mask": mask.numpy()}
+    out["lp_masked"] = label_propagation(labels, norm, 4, 0.75, mask=mask).numpy()
+    out["lp_full"] = label_propagation(labels, norm, 3, 0.5).numpy()
+    np.savez_compressed(os.path.join(OUT, "tricks.npz"), **out)
+    print("wrote tricks", {k: v.shape for k, v in out.items()})
+
+
 if __name__ == "__main__":
     os.makedirs(OUT, exist_ok=True)
-    gen_graph_cases()
-    gen_message_cases()
+    if "--tricks-only" not in sys.argv:
+        gen_graph_cases()
+        gen_message_cases()
+    gen_trick_cases()

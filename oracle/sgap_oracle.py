@@ -413,3 +413,49 @@ def reference_kernel_hop(lib, adj: Csr, x: np.ndarray, a32: Optional[np.ndarray]
     lib.FloatCSRMulDenseOMP(y, a32, adj.indices, indptr32, np.ascontiguousarray(x, dtype=np.float32).reshape(-1),
                             n, d)
     return y.reshape(n, d)
+
+
+# ----------------------------------------------------------------------------------------------------------
+# 8f-3: adjacent consumers (restated for tests/test_gpu_parity.py; tolerance parity -- the reference uses torch.spmm
+# on CPU COO tensors, whose accumulation order is unspecified)
+# ----------------------------------------------------------------------------------------------------------
+def label_propagation(labels: np.ndarray, adj_norm: Csr, num_layers: int, alpha: float, mask=None,
+                      clamp=(0.0, 1.0)) -> np.ndarray:
+    """sgl/tricks/utils.py:40-58 with the default post_process (clamp to [0, 1]); labels already one-hot float32."""
+    lab = np.asarray(labels, dtype=np.float32)
+    out = lab.copy()
+    if mask is not None:
+        out = np.zeros_like(lab)
+        out[mask] = lab[mask]
+    res = np.float32(1 - alpha) * out
+    a32 = Csr(adj_norm.indptr, adj_norm.indices, adj_norm.data.astype(np.float32), adj_norm.shape)
+    for _ in range(num_layers):
+        out = np.float32(alpha) * spmm_hop(a32, out, "muladd") + res
+        if clamp is not None:
+            out = np.clip(out, clamp[0], clamp[1])
+    return out.astype(np.float32)
+
+
+def nafs_smoothed_features(adj, x: np.ndarray, hops: int, r_list=(0.5, 0.4, 0.3, 0.2, 0.1, 0.0), method="mean"):
+    """Feature construction of NodeClusteringNAFS._k_hop_cluster (sgl/tasks/node_clustering.py:205-251): per r the
+    hops of adj_to_symmetric_norm(adj, r) (tasks/utils.py:412-424, same formula as operators/utils.py:76-88), the
+    over-smoothing-distance weights (:226-243, identical to over_smooth_distance_op.py:13-31) and the combination
+    over r (:246-253)."""
+    per_r = []
+    for r in r_list:
+        a = symmetric_norm_csr(adj, r)
+        a32 = Csr(a.indptr, a.indices, a.data.astype(np.float32), a.shape)
+        feats = [np.asarray(x, dtype=np.float32)]
+        for _ in range(hops):
+            feats.append(spmm_hop(a32, feats[-1], "muladd"))
+        if method == "simple":
+            per_r.append(feats[-1])
+            break
+        per_r.append(combine_osd(feats))
+    if method == "mean":
+        return (sum(per_r) / np.float32(len(per_r))).astype(np.float32)
+    if method == "max":
+        return np.stack(per_r, axis=0).max(axis=0)
+    if method == "concat":
+        return np.concatenate(per_r, axis=1)
+    return per_r[-1]

@@ -36,6 +36,8 @@ class GraphOp:
     # "device": subclasses that publish _norm_spec() (r, alpha) get A^ built on the GPU (sgl_b200.graph_build) and
     #           self._adj becomes a lazily downloaded scipy view -- removes the single-core scipy pass from preprocess
     build_on = os.environ.get("SGLB200_BUILD", "host")
+    # directory of the on-disk cache of propagated features (sgl_b200.cache); None = off
+    cache_dir = os.environ.get("SGLB200_CACHE_DIR") or None
 
     def __init__(self, prop_steps):
         self._prop_steps = prop_steps
@@ -97,6 +99,27 @@ class GraphOp:
         return self._operator.propagate(x, self._prop_steps, mode=self.mode, concat=concat)
 
     def propagate(self, adj, feature):
+        if self.cache_dir and isinstance(adj, sp.csr_matrix) and isinstance(feature, (np.ndarray, Tensor)) \
+                and adj.shape[1] == feature.shape[0]:
+            return self._propagate_cached(adj, feature)
+        return self._propagate_uncached(adj, feature)
+
+    def _propagate_cached(self, adj, feature):
+        from ..cache import HopCache
+        spec = self._norm_spec()
+        params = {"r": spec[0], "alpha": spec[1]} if spec is not None else {}
+        cache = HopCache(self.cache_dir)
+        key = cache.key(adj, feature, type(self).__name__ + ":" + self.mode, self._prop_steps, **params)
+        hops = cache.load(key)
+        if hops is not None:
+            first = torch.from_numpy(feature) if isinstance(feature, np.ndarray) else feature.detach().float().cpu()
+            hops = [first] + hops[1:]
+            return [h.cuda() for h in hops] if self.output_device == "cuda" else hops
+        hops = self._propagate_uncached(adj, feature)
+        cache.save(key, hops)
+        return hops
+
+    def _propagate_uncached(self, adj, feature):
         if getattr(self, "_prepared_for", None) is adj and self._operator is not None \
                 and isinstance(feature, (np.ndarray, Tensor)) and feature.shape[0] == self._operator.shape[1]:
             hops = self.propagate_device(adj, feature)

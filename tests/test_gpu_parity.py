@@ -538,3 +538,28 @@ def test_tile_ranges_compose_to_the_full_hop():
             assert torch.equal(done, full[:rows[c + 1]])       # rows finished so far are final
         assert torch.equal(out, full)
     op.close()
+
+
+# --------------------------------------------------------------------------------------------------------------
+# 8f-3: label propagation and the NAFS task-level feature construction on the same handle
+# --------------------------------------------------------------------------------------------------------------
+def test_label_propagation_and_nafs_features():
+    from sgl_b200.operators.utils import adj_to_symmetric_norm
+    from sgl_b200.tricks import label_propagation, nafs_smoothed_features
+    rng = np.random.default_rng(47)
+    n, classes = 3000, 7
+    adj = random_graph(rng, n, 25000)
+    y = torch.from_numpy(rng.integers(0, classes, n))
+    mask = torch.from_numpy(rng.random(n) < 0.3)
+    norm = adj_to_symmetric_norm(adj, 0.5)
+    got = label_propagation(y, norm, num_layers=5, alpha=0.8, mask=mask)
+    onehot = np.eye(classes, dtype=np.float32)[y.numpy()]
+    want = O.label_propagation(onehot, O.laplacian_adj(adj, 0.5), 5, 0.8, mask=mask.numpy())
+    assert got.shape == (n, classes) and not got.is_cuda
+    np.testing.assert_allclose(got.numpy(), want, rtol=1e-5, atol=1e-6)
+    x = rng.standard_normal((n, 64)).astype(np.float32)
+    for method in ("mean", "max", "concat", "simple"):
+        got = nafs_smoothed_features(adj, x, hops=3, r_list=(0.5, 0.3, 0.0), method=method).numpy()
+        want = O.nafs_smoothed_features(adj, x, 3, (0.5, 0.3, 0.0), method)
+        assert got.shape == want.shape
+        np.testing.assert_allclose(got, want, rtol=2e-5, atol=4e-6, err_msg=method)

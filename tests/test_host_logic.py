@@ -169,3 +169,30 @@ def test_device_builder_passes_match_reference(path, tag, kind, r, alpha):
         assert np.array_equal(v.astype(np.float32), ref.astype(np.float32))
     else:
         assert np.array_equal(v, ref)
+
+
+def test_hop_cache_round_trip_and_content_keys(tmp_path):
+    from sgl_b200.cache import HopCache
+    rng = np.random.default_rng(0)
+    adj = sp.random(50, 50, density=0.1, format="csr", random_state=1, dtype=np.float32)
+    x = rng.standard_normal((50, 8)).astype(np.float32)
+    hops = [torch.from_numpy(x)] + [torch.from_numpy(rng.standard_normal((50, 8)).astype(np.float32)) for _ in range(3)]
+    cache = HopCache(str(tmp_path))
+    key = cache.key(adj, x, "LaplacianGraphOp:fast", 3, r=0.5, alpha=None)
+    assert cache.load(key) is None
+    cache.save(key, hops)
+    back = cache.load(key)
+    assert len(back) == 4 and all(torch.equal(a, b) for a, b in zip(back, hops))
+    # any change of the inputs changes the key
+    assert cache.key(adj, x, "LaplacianGraphOp:fast", 4, r=0.5, alpha=None) != key
+    assert cache.key(adj, x, "LaplacianGraphOp:fast", 3, r=0.3, alpha=None) != key
+    assert cache.key(adj, x + 1, "LaplacianGraphOp:fast", 3, r=0.5, alpha=None) != key
+    adj2 = adj.copy()
+    adj2.data[0] += 1
+    assert cache.key(adj2, x, "LaplacianGraphOp:fast", 3, r=0.5, alpha=None) != key
+    # a cache hit is served without a GPU (this test runs with -m "not gpu")
+    op = LaplacianGraphOp(3, r=0.5)
+    op.cache_dir = str(tmp_path)
+    HopCache(str(tmp_path)).save(HopCache.key(adj, x, "LaplacianGraphOp:" + op.mode, 3, r=0.5, alpha=None), hops)
+    got = op.propagate(adj, x)
+    assert all(torch.equal(a, b) for a, b in zip(got, hops)) and got[0].data_ptr() == torch.from_numpy(x).data_ptr()

@@ -105,3 +105,13 @@ def test_empty_and_ragged_rows():
     np.testing.assert_allclose(y, dense @ x)
     with pytest.raises(ValueError):
         O.spmm_hop(adj, np.zeros((5, 2), dtype=np.float32))
+
+
+def test_label_propagation_matches_reference():
+    from conftest import GOLDEN
+    g = dict(np.load(os.path.join(GOLDEN, "tricks.npz")))
+    z, adj = load_graph(os.path.join(GOLDEN, "graph_skewed200.npz"))
+    a = O.laplacian_adj(adj, 0.5)
+    onehot = np.eye(int(g["labels"].max()) + 1, dtype=np.float32)[g["labels"]]
+    np.testing.assert_allclose(O.label_propagation(onehot, a, 4, 0.75, mask=g["mask"]), g["lp_masked"], rtol=1e-6, atol=1e-7)
+    np.testing.assert_allclose(O.label_propagation(onehot, a, 3, 0.5), g["lp_full"], rtol=1e-6, atol=1e-7)
