@@ -315,9 +315,12 @@ class DistOperator:
         p = self.plan
         src = ps.slabs[which]
         stream = ctypes_void(torch.cuda.current_stream().cuda_stream)
-        for q in range(p.world):
+        # staggered peer order (rank+1, rank+2, ...): at every step each receiver has exactly one sender, instead of all
+        # ranks storing into rank 0 first (incast on one NVLink port: measured 195 GB/s per sender at 8 GPUs)
+        for step in range(1, p.world):
+            q = (p.rank + step) % p.world
             rows = self._send_per_peer[c][q]
-            if q == p.rank or rows.numel() == 0:
+            if rows.numel() == 0:
                 continue
             _lib.check(lib.sglb200_push_rows(ctypes_void(src.data_ptr()), ps.d, ps.d, ctypes_void(rows.data_ptr()),
                                              int(rows.numel()), ctypes_void(ps.peer_slab_ptr(q, which, self._dst_row[c][q])),
