@@ -16,6 +16,41 @@ from torch import Tensor
 from ..runtime import CsrOperator, require_cuda
 
 
+def propagate_reference_contract(op, adj, feature):
+    """The body of GraphOp.propagate with the reference's exact contract (base_op.py:19-36): build A^ with the
+    operator's own `_construct_adj`, validate, run the K hops on the GPU.  `op` may be one of our GraphOp objects or an
+    instance of the reference's own classes (sgl_b200.patch binds this function to sgl.operators.base_op.GraphOp)."""
+    op._adj = op._construct_adj(adj)
+
+    if not isinstance(adj, sp.csr_matrix):
+        raise TypeError("The adjacency matrix must be a scipy csr sparse matrix!")
+    elif not isinstance(feature, (np.ndarray, Tensor)):
+        raise TypeError("The feature matrix must be a numpy.ndarray!")
+    elif op._adj.shape[1] != feature.shape[0]:
+        raise ValueError("Dimension mismatch detected for the adjacency and the feature matrix!")
+
+    if isinstance(feature, Tensor):
+        first = feature.detach()
+        first = first if first.dtype == torch.float32 else first.float()
+    else:
+        if feature.dtype != np.float32:
+            # the reference's ctypes signature rejects anything but float32 (utils.py:21-25)
+            raise TypeError("The feature matrix must be a float32 numpy.ndarray!")
+        first = torch.from_numpy(feature)  # shares memory, like torch.FloatTensor(ndarray) at base_op.py:36
+    require_cuda()
+
+    previous = getattr(op, "_operator", None)
+    if previous is not None:
+        previous.close()
+    op._operator = CsrOperator.from_scipy(op._adj)
+    mode = getattr(op, "mode", "fast")
+    steps = op._prop_steps
+    if getattr(op, "output_device", "cpu") == "cuda":
+        return op._operator.propagate(first.cuda(), steps, mode=mode)
+    rest = op._operator.propagate_host(first.cpu(), steps, mode=mode, keep="all")
+    return [first.cpu()] + rest
+
+
 class GraphOp:
     """K-hop propagation  [X, A^X, ..., A^^K X]  of a normalised adjacency A^ built by ``_construct_adj``.
 
@@ -132,35 +167,7 @@ class GraphOp:
         if spec is not None and isinstance(adj, sp.csr_matrix) and isinstance(feature, (np.ndarray, Tensor)) \
                 and adj.shape[1] == feature.shape[0]:
             return self._propagate_device_built(adj, feature, spec)
-        self._adj = self._construct_adj(adj)
-
-        if not isinstance(adj, sp.csr_matrix):
-            raise TypeError("The adjacency matrix must be a scipy csr sparse matrix!")
-        elif not isinstance(feature, (np.ndarray, Tensor)):
-            raise TypeError("The feature matrix must be a numpy.ndarray!")
-        elif self._adj.shape[1] != feature.shape[0]:
-            raise ValueError("Dimension mismatch detected for the adjacency and the feature matrix!")
-
-        if isinstance(feature, Tensor):
-            first = feature.detach()
-            first = first if first.dtype == torch.float32 else first.float()
-        else:
-            if feature.dtype != np.float32:
-                # the reference's ctypes signature rejects anything but float32 (utils.py:21-25)
-                raise TypeError("The feature matrix must be a float32 numpy.ndarray!")
-            first = torch.from_numpy(feature)  # shares memory, like torch.FloatTensor(ndarray) at base_op.py:36
-        require_cuda()
-
-        if self._operator is not None:
-            self._operator.close()
-        self._operator = CsrOperator.from_scipy(self._adj)
-
-        if self.output_device == "cuda":
-            hops = self._operator.propagate(first.cuda(), self._prop_steps, mode=self.mode)
-            return hops
-        rest = self._operator.propagate_host(first.cpu(), self._prop_steps, mode=self.mode, keep="all")
-        return [first.cpu()] + rest
-
+        return propagate_reference_contract(self, adj, feature)
 
     def _propagate_device_built(self, adj, feature, spec):
         from ..graph_build import operator_from_scipy_device

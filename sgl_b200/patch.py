@@ -36,10 +36,8 @@ def install():
     _saved["matmul_base"] = ref_base.csr_sparse_dense_matmul
 
     def propagate(self, adj, feature):
-        # same body as ours, bound to the reference class: self._construct_adj is the reference's own
-        if not hasattr(self, "_operator"):
-            self._operator = None
-        return ours_base.GraphOp.propagate(self, adj, feature)
+        # the reference contract, bound to the reference class: self._construct_adj stays the reference's own
+        return ours_base.propagate_reference_contract(self, adj, feature)
 
     ref_base.GraphOp.propagate = propagate
     ref_base.GraphOp.mode = ours_base.GraphOp.mode
