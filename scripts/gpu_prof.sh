@@ -3,7 +3,7 @@
 TAG=${1:-prof}; shift
 OUT=gpurun_out/$TAG
 mkdir -p $OUT
-ncu --metrics gpu__time_duration.sum --clock-control none -k regex:sglb200 -c 300 --csv --log-file $OUT/launches.csv \
+ncu --metrics gpu__time_duration.sum --clock-control none -k regex:spmm_\|agg_\|normalize_values\|build_tiles\|carry_runs -c 300 --csv --log-file $OUT/launches.csv \
     python bench.py --steps 2 --warmup 3 --no-cpu-baseline --no-e2e "$@" > $OUT/ncu_bench.log 2>&1
 echo "ncu list exit $?"
 ncu --set full --clock-control none --import-source on -k regex:spmm_flat_kernel -s 20 -c 2 -o $OUT/spmm_full \
