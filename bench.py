@@ -473,6 +473,34 @@ def run_dist(args):
     total_s = float(mine.item())
     recv = torch.tensor([float(exchange_volume_bytes(plan, d))], device=dev, dtype=torch.float64)
     dist.all_reduce(recv, op=dist.ReduceOp.MAX)
+    # end to end at N GPUs: every rank uploads its row shard of X from pinned host memory, the K partitioned hops run,
+    # and the rank's rows of the last hop (what SGC's LastMessageOp consumes) come back into pinned host memory
+    e2e = None
+    if not args.no_e2e:
+        x_pin = x_full[lo:hi].clone().pin_memory()
+        y_pin = torch.empty((hi - lo, d), dtype=torch.float32, pin_memory=True)
+        e2e_steps = max(3, min(args.steps, 10))
+
+        def e2e_step():
+            xd = x_pin.to(dev, non_blocking=True)
+            last = op.propagate(xd, K, keep="last")[-1]
+            y_pin.copy_(last, non_blocking=True)
+            torch.cuda.current_stream().synchronize()
+
+        for _ in range(2):
+            e2e_step()
+        dist.barrier()
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        for _ in range(e2e_steps):
+            e2e_step()
+        torch.cuda.synchronize()
+        dt = torch.tensor([time.perf_counter() - t0], device=dev, dtype=torch.float64)
+        dist.all_reduce(dt, op=dist.ReduceOp.MAX)
+        e2e = {"value": nnz * K * e2e_steps / float(dt.item()), "unit": UNIT, "h2d_bytes_per_step": n * d * 4,
+               "d2h_bytes_per_step": n * d * 4, "ms_per_step": 1e3 * float(dt.item()) / e2e_steps, "steps": e2e_steps,
+               "api": "DistOperator.propagate per rank: pinned host row shard in -> K partitioned hops -> pinned host rows "
+                      "of hop K out (bytes are whole-job totals)"}
     # parity: this rank's last hop against the oracle chain on sampled local rows, computed from the full input
     ok = 1.0
     if rank == 0:
@@ -497,7 +525,7 @@ def run_dist(args):
                              "algorithmic_bytes_per_launch": b_alg / world, "us_per_launch": hop_s * 1e6,
                              "peak_source": src + " x n_gpus"},
                 "cpu_baseline": None,
-                "e2e": None, "clocks": clocks, "gpu_launches": args.steps * K * 3,
+                "e2e": e2e, "clocks": clocks, "gpu_launches": args.steps * K * 3,
                 "setup": {"build_plan_s": t_build}}
         print(json.dumps(line))
     dist.destroy_process_group()
