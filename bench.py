@@ -534,6 +534,10 @@ def run_dist(args):
 def main():
     args = parse_args()
     if args.impl == "reference":
+        # torchrun exports OMP_NUM_THREADS=1; the reference arm is meant to use every host core it can, and libgomp reads
+        # the variable when it is loaded (before torch / the oracle library are imported below)
+        os.environ["OMP_NUM_THREADS"] = str(os.cpu_count() or 1)
+    if args.impl == "reference":
         run_reference(args)
     else:
         run_b200(args)
