@@ -379,6 +379,37 @@ def run_b200(args):
         assert float(np.abs(outs[-1].numpy()[sample] - got).max()) == 0.0
         model._pre_graph_op._operator.close()
 
+    # ---- GPU comparator: cuSPARSE SpMM (the reference's own dormant GPU choice, csrc/cudamatmul.c:104-119) -------------
+    comparators = {}
+    try:
+        a_t = torch.sparse_csr_tensor(torch.from_numpy(adj_norm.indptr.astype(np.int64)).to(dev),
+                                      torch.from_numpy(adj_norm.indices.astype(np.int64)).to(dev),
+                                      torch.from_numpy(adj_norm.data.astype(np.float32)).to(dev), size=(n, n))
+        cur = hops[0]
+        for _ in range(3):
+            cur = torch.sparse.mm(a_t, hops[0])
+        torch.cuda.synchronize()
+        c_steps = max(3, min(args.steps, 10))
+        ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        ms = 0.0
+        for i in range(c_steps):
+            flush.fill_(i & 0xFF)
+            ev0.record(stream)
+            cur = hops[0]
+            for _ in range(K):
+                cur = torch.sparse.mm(a_t, cur)
+            ev1.record(stream)
+            torch.cuda.synchronize()
+            ms += ev0.elapsed_time(ev1)
+        err = float((cur - hops[K]).abs().max() / hops[K].abs().max())
+        comparators["cusparse_spmm_via_torch"] = {"value": nnz * K * c_steps / (ms / 1e3), "unit": UNIT,
+                                                   "us_per_hop": 1e3 * ms / (c_steps * K), "max_rel_diff_vs_ours": err,
+                                                   "note": "torch.sparse.mm on a CSR tensor (cuSPARSE SpMM), device resident, "
+                                                           "same graph and features; a library call, reported for context"}
+        del a_t, cur
+    except Exception as exc:  # the comparator must never break the bench line
+        comparators["cusparse_spmm_via_torch"] = {"unavailable": str(exc)[:200]}
+
     cpu = None
     if not args.no_cpu_baseline:
         times, kind, threads = cpu_reference_steps(adj_norm, x_host.numpy(), K, steps=3, warmup=1, budget_s=25.0)
@@ -389,7 +420,8 @@ def run_b200(args):
     line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": 1, "steps": args.steps, "warmup": max(args.warmup, 3),
             "ms_per_step": 1e3 * total_s / args.steps, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
             "dtype": "f32", "data": "synthetic", "config": workload_config(name, n, nnz, d, K, args), "roofline": roofline,
-            "cpu_baseline": cpu, "e2e": e2e, "clocks": clocks, "gpu_launches": launches_per_step * args.steps,
+            "cpu_baseline": cpu, "e2e": e2e, "comparators": comparators, "clocks": clocks,
+            "gpu_launches": launches_per_step * args.steps,
             "parity": {"checked": "every hop vs oracle fma chain on 2000 sampled rows", "max_rel_err": worst},
             "setup": {"generate_s": t_gen, "normalise_host_scipy_s": t_norm, "build_on_device_s": t_upload,
                       "tiles": info["tiles_fast"], "cut_rows": info["carry_runs"], "tile_items": info["tile_items"],
