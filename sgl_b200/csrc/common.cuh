@@ -39,11 +39,14 @@ struct Schedule {
     int32_t *tile_row = nullptr;    // n_tiles+1
     int64_t *tile_nnz = nullptr;    // n_tiles+1
     int32_t *carry_slot = nullptr;  // n_tiles : workspace slot for the partial sum of the row cut by the tile end, -1 none
+    int32_t *tail_run = nullptr;    // n_tiles : run (cut row) that partial belongs to, -1 none
+    int32_t *head_run = nullptr;    // n_tiles : run whose row this tile FINISHES (its first row is a continuation), -1 none
+    uint32_t *run_count = nullptr;  // n_runs  : arrivals of the current hop (self-resetting), in-kernel fold
     int64_t n_runs = 0;             // rows cut across tiles
     int64_t n_slots = 0;            // carry partials in total
     int32_t *run_row = nullptr;     // n_runs
-    int64_t *run_base = nullptr;    // n_runs : first slot
-    int32_t *run_len = nullptr;     // n_runs : consecutive slots
+    int64_t *run_base = nullptr;    // n_runs : first slot (carriers in tile order)
+    int32_t *run_len = nullptr;     // n_runs : number of carrier tiles
     std::vector<int64_t> run_last_tile;  // host copy, sorted: tile that finishes the cut row of run r (runs are
                                          // sorted by row, so a tile range maps to a contiguous run range)
 };

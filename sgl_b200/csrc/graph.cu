@@ -87,7 +87,7 @@ __device__ __forceinline__ int32_t carried_row(const int64_t *indptr, const int3
     return j_end > from ? (int32_t)i_end : -1;
 }
 
-// pass 0: counts[0] += runs, counts[1] += slots.  pass 1: fills run_* and carry_slot using counts[2], counts[3] as cursors.
+// pass 0: counts[0] += runs, counts[1] += carrier tiles.  pass 1: appends (row, carriers, first carrier tile) of every run.
 __global__ void carry_runs_kernel(const int64_t *__restrict__ indptr, const int32_t *__restrict__ tile_row,
                                   const int64_t *__restrict__ tile_nnz, int64_t n_rows, int64_t n_tiles, int pass,
                                   unsigned long long *counts, int32_t *carry_slot, int32_t *run_row, int64_t *run_base,
@@ -105,12 +105,9 @@ __global__ void carry_runs_kernel(const int64_t *__restrict__ indptr, const int3
         atomicAdd(&counts[1], (unsigned long long)len);
     } else {
         const unsigned long long r = atomicAdd(&counts[2], 1ULL);
-        const unsigned long long base = atomicAdd(&counts[3], (unsigned long long)len);
         run_row[r] = row;
-        run_base[r] = (int64_t)base;
         run_len[r] = (int32_t)len;
-        run_head[r] = t;
-        for (int64_t u = 0; u < len; ++u) carry_slot[t + u] = (int32_t)(base + u);
+        run_head[r] = t;  // slots and the per-tile maps are laid out on the host once the runs are sorted
     }
 }
 
@@ -119,6 +116,9 @@ void free_schedule(Schedule *s)
     cudaFree(s->tile_row);
     cudaFree(s->tile_nnz);
     cudaFree(s->carry_slot);
+    cudaFree(s->tail_run);
+    cudaFree(s->head_run);
+    cudaFree(s->run_count);
     cudaFree(s->run_row);
     cudaFree(s->run_base);
     cudaFree(s->run_len);
@@ -167,10 +167,9 @@ int build_schedule(sglb200_graph *g, Schedule *s, int64_t split_threshold, cudaS
             // order the runs by tile (== by row) on the host so that a tile range owns a contiguous run range
             const size_t nr = (size_t)s->n_runs;
             std::vector<int32_t> h_row(nr), h_len(nr);
-            std::vector<int64_t> h_base(nr), h_head(nr);
+            std::vector<int64_t> h_head(nr);
             if (e == cudaSuccess) e = cudaMemcpyAsync(h_row.data(), s->run_row, nr * 4, cudaMemcpyDeviceToHost, stream);
             if (e == cudaSuccess) e = cudaMemcpyAsync(h_len.data(), s->run_len, nr * 4, cudaMemcpyDeviceToHost, stream);
-            if (e == cudaSuccess) e = cudaMemcpyAsync(h_base.data(), s->run_base, nr * 8, cudaMemcpyDeviceToHost, stream);
             if (e == cudaSuccess) e = cudaMemcpyAsync(h_head.data(), run_head, nr * 8, cudaMemcpyDeviceToHost, stream);
             if (e == cudaSuccess) e = cudaStreamSynchronize(stream);
             cudaFree(run_head);
@@ -180,17 +179,36 @@ int build_schedule(sglb200_graph *g, Schedule *s, int64_t split_threshold, cudaS
             std::sort(order.begin(), order.end(), [&](size_t a, size_t b) { return h_head[a] < h_head[b]; });
             std::vector<int32_t> s_row(nr), s_len(nr);
             std::vector<int64_t> s_base(nr);
+            std::vector<int32_t> t_slot((size_t)n_tiles, -1), t_tail((size_t)n_tiles, -1), t_head((size_t)n_tiles, -1);
             s->run_last_tile.resize(nr);
+            int64_t next_slot = 0;
             for (size_t i = 0; i < nr; ++i) {
                 const size_t o = order[i];
+                const int64_t head = h_head[o];
+                const int32_t len = h_len[o];
                 s_row[i] = h_row[o];
-                s_len[i] = h_len[o];
-                s_base[i] = h_base[o];
-                s->run_last_tile[i] = h_head[o] + h_len[o];  // the tile after the last carrier finishes the row
+                s_len[i] = len;
+                s_base[i] = next_slot;
+                for (int32_t u = 0; u < len; ++u) {
+                    t_slot[(size_t)(head + u)] = (int32_t)(next_slot + u);
+                    t_tail[(size_t)(head + u)] = (int32_t)i;
+                }
+                t_head[(size_t)(head + len)] = (int32_t)i;   // the tile after the last carrier finishes the row
+                s->run_last_tile[i] = head + len;
+                next_slot += len;
             }
+            s->n_slots = next_slot;
+            SGL_CUDA_CHECK(cudaMalloc(&s->tail_run, sizeof(int32_t) * n_tiles));
+            SGL_CUDA_CHECK(cudaMalloc(&s->head_run, sizeof(int32_t) * n_tiles));
+            SGL_CUDA_CHECK(cudaMalloc(&s->run_count, sizeof(uint32_t) * nr));
+            g->bytes_resident += (size_t)n_tiles * 8 + nr * 4;
+            SGL_CUDA_CHECK(cudaMemsetAsync(s->run_count, 0, sizeof(uint32_t) * nr, stream));
             SGL_CUDA_CHECK(cudaMemcpyAsync(s->run_row, s_row.data(), nr * 4, cudaMemcpyHostToDevice, stream));
             SGL_CUDA_CHECK(cudaMemcpyAsync(s->run_len, s_len.data(), nr * 4, cudaMemcpyHostToDevice, stream));
             SGL_CUDA_CHECK(cudaMemcpyAsync(s->run_base, s_base.data(), nr * 8, cudaMemcpyHostToDevice, stream));
+            SGL_CUDA_CHECK(cudaMemcpyAsync(s->carry_slot, t_slot.data(), (size_t)n_tiles * 4, cudaMemcpyHostToDevice, stream));
+            SGL_CUDA_CHECK(cudaMemcpyAsync(s->tail_run, t_tail.data(), (size_t)n_tiles * 4, cudaMemcpyHostToDevice, stream));
+            SGL_CUDA_CHECK(cudaMemcpyAsync(s->head_run, t_head.data(), (size_t)n_tiles * 4, cudaMemcpyHostToDevice, stream));
             SGL_CUDA_CHECK(cudaStreamSynchronize(stream));
         }
         SGL_CUDA_CHECK(cudaStreamSynchronize(stream));

@@ -46,6 +46,15 @@ struct SpmmParams {
     float *carry_ws;
     int64_t ws_ld;
     int stream_y;  // 1: output rows are stored with the streaming (evict-first) policy
+    // in-kernel fold of cut rows (fold != 0): every tile that holds a piece of a cut row stores its partial in the
+    // workspace and arrives on the row's counter; the LAST arriver adds the partials in tile order and writes Y
+    int fold;
+    const int32_t *tail_run;
+    const int32_t *head_run;
+    const int32_t *run_row;
+    const int64_t *run_base;
+    const int32_t *run_len;
+    unsigned int *run_count;
 };
 
 template <int VEC> struct Vec;
@@ -106,6 +115,11 @@ template <> struct Slice<4> {
     __device__ __forceinline__ void zero() { v.x = 0ULL; v.y = 0ULL; }
     __device__ __forceinline__ void load_nc(const char *p) { v = __ldg(reinterpret_cast<const ulonglong2 *>(p)); }
     __device__ __forceinline__ void load(const char *p) { v = *reinterpret_cast<const ulonglong2 *>(p); }
+    __device__ __forceinline__ void load_l2(const char *p) { v = __ldcg(reinterpret_cast<const ulonglong2 *>(p)); }
+    __device__ __forceinline__ void add(const Slice &x)
+    {
+        asm("add.rn.f32x2 %0, %0, %2; add.rn.f32x2 %1, %1, %3;" : "+l"(v.x), "+l"(v.y) : "l"(x.v.x), "l"(x.v.y));
+    }
     __device__ __forceinline__ void store(char *p) const { *reinterpret_cast<ulonglong2 *>(p) = v; }
     // output rows are written once and not re-read by this hop: streaming store, so they do not evict X from L2
     __device__ __forceinline__ void store_streaming(char *p) const
@@ -123,6 +137,8 @@ template <> struct Slice<2> {
     __device__ __forceinline__ void zero() { v = 0ULL; }
     __device__ __forceinline__ void load_nc(const char *p) { v = __ldg(reinterpret_cast<const unsigned long long *>(p)); }
     __device__ __forceinline__ void load(const char *p) { v = *reinterpret_cast<const unsigned long long *>(p); }
+    __device__ __forceinline__ void load_l2(const char *p) { v = __ldcg(reinterpret_cast<const unsigned long long *>(p)); }
+    __device__ __forceinline__ void add(const Slice &x) { asm("add.rn.f32x2 %0, %0, %1;" : "+l"(v) : "l"(x.v)); }
     __device__ __forceinline__ void store(char *p) const { *reinterpret_cast<unsigned long long *>(p) = v; }
     __device__ __forceinline__ void store_streaming(char *p) const
     {
@@ -138,6 +154,8 @@ template <> struct Slice<1> {
     __device__ __forceinline__ void zero() { v = 0.0f; }
     __device__ __forceinline__ void load_nc(const char *p) { v = __ldg(reinterpret_cast<const float *>(p)); }
     __device__ __forceinline__ void load(const char *p) { v = *reinterpret_cast<const float *>(p); }
+    __device__ __forceinline__ void load_l2(const char *p) { v = __ldcg(reinterpret_cast<const float *>(p)); }
+    __device__ __forceinline__ void add(const Slice &x) { v = __fadd_rn(v, x.v); }
     __device__ __forceinline__ void store(char *p) const { *reinterpret_cast<float *>(p) = v; }
     __device__ __forceinline__ void store_streaming(char *p) const
     {
@@ -330,6 +348,48 @@ __global__ void __launch_bounds__(kWarpsPerBlock * 32, MINB) spmm_flat_kernel(co
 #pragma unroll
         for (int v = 0; v < VPL; ++v)
             if (act[v]) acc[v].store(wrow + (size_t)(col_block + (v * 32 + lane) * VEC) * sizeof(float));
+    }
+    // in-kernel fold of cut rows (epilogue: nothing of the hot loop is live here).  A tile can be the FINISHER of one cut
+    // row (its first row continued an earlier tile: the partial already sits in Y) and a CARRIER of another (the partial
+    // just stored above).  Every participant arrives on the row's counter after a device-wide fence; the last arriver
+    // adds the carriers in tile order to the finisher's partial -- the same sum, in the same order, whoever folds.
+    if (p.fold) {
+        const int finishes = p.head_run[t];
+        const int carries = slot >= 0 ? p.tail_run[t] : -1;
+        if (finishes >= 0 || carries >= 0) {
+            __threadfence();
+            __syncwarp();
+#pragma unroll 1
+            for (int role = 0; role < 2; ++role) {
+                const int run = role == 0 ? finishes : carries;
+                if (run < 0) continue;
+                const int n_carriers = p.run_len[run];
+                unsigned int seen = 0;
+                if (lane == 0) seen = atomicAdd(p.run_count + run, 1u);
+                seen = __shfl_sync(kFull, seen, 0);
+                if (seen != (unsigned int)n_carriers) continue;  // someone else will arrive later and fold
+                __threadfence();
+                const char *ws0 = reinterpret_cast<const char *>(p.carry_ws + p.run_base[run] * p.ws_ld);
+                const size_t ws_ld_bytes = (size_t)p.ws_ld * sizeof(float);
+                const uint32_t out_row = (uint32_t)p.run_row[run];
+#pragma unroll
+                for (int v = 0; v < VPL; ++v) {
+                    if (!act[v]) continue;
+                    const size_t cb = (size_t)(col_block + (v * 32 + lane) * VEC) * sizeof(float);
+                    Slice<VEC> sum, part;
+                    sum.load_l2(ws0 + cb);
+                    for (int u = 1; u < n_carriers; ++u) {
+                        part.load_l2(ws0 + (size_t)u * ws_ld_bytes + cb);
+                        sum.add(part);
+                    }
+                    char *yp = ybase[v] + (uint64_t)out_row * ldy_bytes;
+                    part.load_l2(yp);          // the finishing tile's partial
+                    part.add(sum);             // Y = finisher + (c0 + c1 + ...): the order of the separate fold kernel
+                    part.store(yp);
+                }
+                if (lane == 0) p.run_count[run] = 0u;  // ready for the next hop
+            }
+        }
     }
 }
 
@@ -661,6 +721,22 @@ int spmm_launch_tiles(sglb200_graph *g, const float *X, int64_t ldx, float *Y, i
     p.carry_ws = g->carry_ws;
     p.ws_ld = ws_ld;
     {
+        // cut rows are folded inside the hop kernel by the last tile that arrives (default); SGLB200_FOLD=fixup keeps
+        // the separate fold launch (also used by the cp.async ring variant, which does not carry the arrival logic)
+        static int fold_mode = -1;
+        if (fold_mode < 0) {
+            const char *e = getenv("SGLB200_FOLD");
+            fold_mode = (e && e[0] == 'f') ? 0 : 1;
+        }
+        p.fold = (fold_mode == 1 && s->n_runs > 0 && spmm_variant() < 10) ? 1 : 0;
+        p.tail_run = s->tail_run;
+        p.head_run = s->head_run;
+        p.run_row = s->run_row;
+        p.run_base = s->run_base;
+        p.run_len = s->run_len;
+        p.run_count = s->run_count;
+    }
+    {
         // X (n_cols x d) should own L2 during a hop: stream Y past it unless Y is small enough to stay resident too
         static int force = -2;
         if (force == -2) {
@@ -730,7 +806,7 @@ int spmm_launch_tiles(sglb200_graph *g, const float *X, int64_t ldx, float *Y, i
     }
 #undef SGL_SHAPE
     SGL_CUDA_CHECK(e);
-    if (s->n_runs > 0) {
+    if (s->n_runs > 0 && !p.fold) {
         // runs are sorted by tile: those whose finishing tile lies in [tile_begin, tile_end) form one contiguous range
         const auto &last = s->run_last_tile;
         const int64_t r0 = std::lower_bound(last.begin(), last.end(), tile_begin) - last.begin();
