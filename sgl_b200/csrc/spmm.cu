@@ -728,7 +728,8 @@ int spmm_launch_tiles(sglb200_graph *g, const float *X, int64_t ldx, float *Y, i
             const char *e = getenv("SGLB200_FOLD");
             fold_mode = (e && e[0] == 'f') ? 0 : 1;
         }
-        p.fold = (fold_mode == 1 && s->n_runs > 0 && spmm_variant() < 10) ? 1 : 0;
+        // one counter per cut row: valid while a tile is one participant, i.e. a single column block (d <= 512)
+        p.fold = (fold_mode == 1 && s->n_runs > 0 && spmm_variant() < 10 && col_blocks == 1) ? 1 : 0;
         p.tail_run = s->tail_run;
         p.head_run = s->head_run;
         p.run_row = s->run_row;
