@@ -416,7 +416,9 @@ def run_b200(args):
         cpu = {"value": nnz * K * len(times) / float(np.sum(times)), "unit": UNIT, "cores": threads, "kind": kind,
                "sample": f"full workload, {len(times)} steps of K={K} hops after 1 warm-up, bare kernel"}
 
-    launches_per_step = K * (1 + (1 if info["carry_runs"] > 0 and args.mode == "fast" else 0))
+    # cut rows are folded inside the hop kernel (one launch per hop) unless the separate fold launch is selected
+    separate_fold = os.environ.get("SGLB200_FOLD", "kernel").startswith("f") or d > 512
+    launches_per_step = K * (1 + (1 if info["carry_runs"] > 0 and args.mode == "fast" and separate_fold else 0))
     line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": 1, "steps": args.steps, "warmup": max(args.warmup, 3),
             "ms_per_step": 1e3 * total_s / args.steps, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
             "dtype": "f32", "data": "synthetic", "config": workload_config(name, n, nnz, d, K, args), "roofline": roofline,
