@@ -8,14 +8,18 @@
 //     (row ends + non-zeros) stream, so hubs and empty rows cost the same as anything else -- the reference's
 //     static OpenMP row split (matmul.c:25) serialises on skewed graphs;
 //   * a warp walks its non-zero range as ONE flat stream: 32 (col, val) pairs are fetched with one coalesced
-//     streaming load each, then broadcast by shuffle; all 32 lanes hold disjoint 128-bit column slices of the
-//     same output row, so one warp-wide LDG.128 moves a whole 512 B feature row of X (d = 128);
+//     streaming load each and published as 8-byte pairs in shared memory (one LDS.128 broadcast = two pairs for
+//     every lane); all 32 lanes hold disjoint 128-bit column slices of the same output row, so one warp-wide
+//     LDG.128 moves a whole 512 B feature row of X (d = 128);
 //   * U gathered rows are in flight per warp before the first FMA consumes them (memory-level parallelism);
-//   * row boundaries are warp-uniform branches against a shuffle-distributed prefetch of 32 row ends;
+//   * accumulation in packed fp32 pairs (fma.rn.f32x2 -> FFMA2), bit-identical to scalar fmaf;
+//   * a group of U non-zeros inside one row takes a check-free path; otherwise row boundaries are warp-uniform
+//     compares against a shuffle-distributed prefetch of 32 row ends;
 //   * per output element the additions happen in CSR order with one fused multiply-add per term: for rows that
 //     are not cut (all rows in the EXACT schedule) this IS the reference's chain, bit for bit;
 //   * rows cut across warps (FAST schedule, rows longer than split_threshold) leave partial sums in a small
-//     workspace that a second kernel folds in tile order -- deterministic, no atomics.
+//     workspace; the tile whose arrival completes a row's counter folds them in tile order in the kernel's
+//     epilogue (deterministic; nothing waits on anything).  spmm_carry_fixup_kernel is the separate-launch form.
 #include <limits.h>
 #include <stdlib.h>
 
@@ -56,11 +60,6 @@ struct SpmmParams {
     const int32_t *run_len;
     unsigned int *run_count;
 };
-
-template <int VEC> struct Vec;
-template <> struct Vec<1> { using type = float; };
-template <> struct Vec<2> { using type = float2; };
-template <> struct Vec<4> { using type = float4; };
 
 // gathered feature rows: read-only path, L1-allocating (hub rows of skewed graphs are re-read by neighbouring warps)
 template <int VEC> __device__ __forceinline__ void load_row_slice(float (&r)[VEC], const float *p)

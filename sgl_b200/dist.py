@@ -4,19 +4,22 @@ The reference has no parallelism on this path (its only collective is DDP of the
 sgl/tasks/node_classification_dist.py:61-70).  Here rank p owns the contiguous row range [b_p, b_{p+1}) of A^ and
 of every feature slab; hop k needs X_{k-1}[j] for every column j its rows reference.  Two exchange plans:
 
-  "halo"      (default) only the rows a rank actually references travel: a packed all-to-all-v of de-duplicated
-              remote rows (torch.distributed.all_to_all_single over NCCL), received straight behind the local shard;
+  "halo"      (default) only the rows a rank actually references travel, de-duplicated, received straight behind the
+              local shard of an "extended" feature slab.  Transport "peer" (default on CUDA): our own kernels store
+              the rows into the peers' slabs over NVLink (CUDA IPC memory, sgl_b200/csrc/peer.cu), pipelined against
+              the hop itself in `n_chunks` tile ranges; transport "nccl": pack + all_to_all_single;
   "allgather" every rank receives every shard (torch.distributed.all_gather_into_tensor) -- what north_star names,
               kept as the simple fallback and as the comparison the halo plan is measured against.
 
 Column ids are renumbered once at construction: local columns -> [0, n_local), remote columns -> n_local + position
-in the receive buffer (halo) or rank*max_rows + offset (allgather, shards padded to equal length).  The per-hop
-arithmetic is the single-GPU kernel on a rectangular operator (sglb200_spmm); row order inside a row is preserved
-for the local block and grouped by owner rank for remote columns, so results equal the single-GPU FAST-mode result
-up to the re-association tolerance (1e-5), and are independent of the exchange plan.
+in the receive layout (halo: chunk-major, then peer, then row) or rank*max_rows + offset (allgather, shards padded to
+equal length).  The per-hop arithmetic is the single-GPU kernel on a rectangular operator (sglb200_spmm /
+sglb200_spmm_tiles).  The storage order of the non-zeros of a row is not changed by the renumbering, so EXACT-mode
+results are bit-identical to the single-GPU result and independent of plan and transport; FAST mode differs only by
+where long rows are cut (tolerance 1e-5).
 
-Everything that does not touch CUDA (partitioning, plans, renumbering) is plain numpy and is exercised on CPU with
-the gloo backend (tests/test_dist_cpu.py).
+Everything that does not touch CUDA (partitioning, plans, renumbering, chunk bounds) is plain numpy and is exercised on
+CPU with the gloo backend (tests/test_dist_cpu.py).
 """
 from __future__ import annotations
 
