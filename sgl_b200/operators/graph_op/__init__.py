@@ -1,4 +1,7 @@
-from .laplacian_graph_op import LaplacianGraphOp
-from .ppr_graph_op import PprGraphOp
+"""Graph operators of the SGAP propagation step (mirror of the reference package sgl.operators.graph_op)."""
+from . import laplacian_graph_op as _lap, ppr_graph_op as _ppr
 
-__all__ = ["LaplacianGraphOp", "PprGraphOp"]
+LaplacianGraphOp = _lap.LaplacianGraphOp
+PprGraphOp = _ppr.PprGraphOp
+
+__all__ = sorted(name for name in dir() if name.endswith("GraphOp"))

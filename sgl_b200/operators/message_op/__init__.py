@@ -1,19 +1,13 @@
-"""Mirror of the reference's sgl/operators/message_op package (same eleven class names)."""
-from .simple_ops import (ConcatMessageOp, LastMessageOp, MaxMessageOp, MeanMessageOp, MinMessageOp,
-                         OverSmoothDistanceWeightedOp, SimpleWeightedMessageOp, SumMessageOp)
-from .learnable_ops import (IterateLearnableWeightedMessageOp, LearnableWeightedMessageOp,
-                            ProjectedConcatMessageOp)
+"""Cross-hop message operators (mirror of the reference package sgl.operators.message_op: the same eleven names)."""
+from . import learnable_ops as _learnable, simple_ops as _simple
 
-__all__ = [
-    "ConcatMessageOp",
-    "IterateLearnableWeightedMessageOp",
-    "LastMessageOp",
-    "LearnableWeightedMessageOp",
-    "MaxMessageOp",
-    "MeanMessageOp",
-    "MinMessageOp",
-    "ProjectedConcatMessageOp",
-    "SimpleWeightedMessageOp",
-    "SumMessageOp",
-    "OverSmoothDistanceWeightedOp",
-]
+_EXPORTS = {
+    _simple: ("LastMessageOp", "SumMessageOp", "MeanMessageOp", "MaxMessageOp", "MinMessageOp", "ConcatMessageOp",
+              "SimpleWeightedMessageOp", "OverSmoothDistanceWeightedOp"),
+    _learnable: ("LearnableWeightedMessageOp", "IterateLearnableWeightedMessageOp", "ProjectedConcatMessageOp"),
+}
+for _module, _names in _EXPORTS.items():
+    for _name in _names:
+        globals()[_name] = getattr(_module, _name)
+
+__all__ = [n for names in _EXPORTS.values() for n in names]
