@@ -49,3 +49,21 @@ def test_argument_validation_without_gpu():
     st = lib.sglb200_graph_create(None, 1, 1, 0, None, 1, None, None, 0, 0, 0, None)
     assert st == _lib.ERR_INVALID
     assert "NULL" in _lib.last_error()
+
+
+def test_header_is_valid_c_and_cpp():
+    """The boundary is a C ABI: the header must compile as plain C (and as C++) without any CUDA or torch include."""
+    import subprocess
+    import tempfile
+    inc = os.path.join(ROOT, "include")
+    for lang, comp, std in (("c", "gcc", "-std=c99"), ("c++", "g++", "-std=c++11")):
+        with tempfile.NamedTemporaryFile("w", suffix=".c" if lang == "c" else ".cpp", delete=False) as f:
+            f.write('#include "sglb200.h"\nint main(void) { return SGLB200_VERSION == sglb200_version() ? 0 : 1; }\n')
+            src = f.name
+        try:
+            exe = "/usr/bin/" + comp if os.path.exists("/usr/bin/" + comp) else comp
+            r = subprocess.run([exe, std, "-Wall", "-Wextra", "-pedantic", "-fsyntax-only", "-I", inc, src],
+                               capture_output=True, text=True)
+            assert r.returncode == 0, r.stderr
+        finally:
+            os.unlink(src)

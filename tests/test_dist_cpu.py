@@ -112,3 +112,37 @@ def test_distributed_propagate_matches_single_process(tmp_path, world, mode, chu
     for r in range(world):
         got = np.load(tmp_path / f"hops_{mode}_{r}.npy")
         assert np.array_equal(got, ref[:, bounds[r]:bounds[r + 1]])
+
+
+def _brute_force_rows_before(indptr, item_pos):
+    """Walk the merged (row ends + non-zeros) stream item by item: rows whose end marker lies in the first item_pos items."""
+    n = len(indptr) - 1
+    done, pos, j = 0, 0, 0
+    for r in range(n):
+        # non-zeros of row r, then its end marker
+        pos += indptr[r + 1] - indptr[r]
+        if pos >= item_pos:
+            return done
+        pos += 1
+        if pos > item_pos:
+            return done
+        done += 1
+    return done
+
+
+def test_chunk_row_bounds_against_item_walk():
+    rng = np.random.default_rng(12)
+    for trial in range(20):
+        n = int(rng.integers(1, 400))
+        deg = rng.integers(0, 40, n) * (rng.random(n) < 0.7)
+        if trial % 4 == 0:
+            deg[rng.integers(0, n)] = 3000            # a hub longer than several tiles
+        indptr = np.concatenate([[0], np.cumsum(deg)]).astype(np.int64)
+        for tile_items in (32, 256):
+            for n_chunks in (1, 2, 5):
+                got = chunk_row_bounds(indptr, n_chunks, tile_items)
+                total = n + int(indptr[-1])
+                n_tiles = (total + tile_items - 1) // tile_items
+                want = [0] + [_brute_force_rows_before(indptr, min((n_tiles * c // n_chunks) * tile_items, total))
+                              for c in range(1, n_chunks)] + [n]
+                assert list(got) == want, (trial, tile_items, n_chunks)
