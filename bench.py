@@ -56,6 +56,8 @@ def parse_args():
     ap.add_argument("--exchange", default="halo", choices=["halo", "allgather"])
     ap.add_argument("--transport", default="peer", choices=["peer", "nccl"],
                     help="halo rows move by our NVLink peer-store kernels (CUDA IPC) or by NCCL all_to_all")
+    ap.add_argument("--plan", default="replicated", choices=["replicated", "collective"],
+                    help="halo plan from the full matrix on every rank (numpy) or built collectively from local rows (torch)")
     ap.add_argument("--chunks", type=int, default=4, help="row chunks the hop is pipelined over against its halo exchange")
     return ap.parse_args()
 
@@ -470,7 +472,16 @@ def run_dist(args):
     torch.cuda.empty_cache()
     # small shards are launch-bound: pipelining them in chunks only adds launches (measured: arxiv-shape on 4 GPUs)
     n_chunks = args.chunks if nnz // world >= 8_000_000 else 1
-    plan = build_plan(indptr, indices, data, n, world, rank, args.exchange, n_chunks=n_chunks)
+    if args.plan == "collective" and args.exchange == "halo":
+        from sgl_b200.dist import build_plan_collective, partition_rows
+        bounds = partition_rows(indptr, world)
+        b0, b1 = int(bounds[rank]), int(bounds[rank + 1])
+        j0, j1 = int(indptr[b0]), int(indptr[b1])
+        plan = build_plan_collective(torch.from_numpy(indptr[b0:b1 + 1] - indptr[b0]).to(dev),
+                                     torch.from_numpy(indices[j0:j1].astype(np.int64)).to(dev),
+                                     torch.from_numpy(data[j0:j1]).to(dev), bounds, n_chunks=n_chunks)
+    else:
+        plan = build_plan(indptr, indices, data, n, world, rank, args.exchange, n_chunks=n_chunks)
     t_build = time.perf_counter() - t0
     op = DistOperator(plan, device=dev, mode=args.mode)
     lo, hi = int(plan.bounds[rank]), int(plan.bounds[rank + 1])

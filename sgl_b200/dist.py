@@ -170,6 +170,84 @@ def build_plan(indptr, indices, data, n_cols: int, world: int, rank: int, mode: 
                     send_rows, recv_counts, crb[rank], 0)
 
 
+def build_plan_collective(loc_ptr, cols, vals, bounds, n_chunks: int = 1, group=None) -> RankPlan:
+    """Halo plan built COLLECTIVELY from each rank's own rows only: no rank needs the full matrix.
+
+    loc_ptr [n_local+1], cols [nnz_local] (GLOBAL column ids), vals [nnz_local]: torch tensors on the device the
+    process group communicates with (CUDA for NCCL, CPU for gloo); bounds: the global row bounds (numpy, length
+    world+1).  The receive side (what this rank references) is a device-side unique / searchsorted pass; the send
+    side (what every peer references here) arrives through one all-to-all of the reference lists.  Produces exactly the
+    plan build_plan() derives from the full matrix (tests/test_dist_cpu.py)."""
+    rank, world = dist.get_rank(group), dist.get_world_size(group)
+    dev = cols.device
+    C = max(1, int(n_chunks))
+    bounds = np.asarray(bounds, dtype=np.int64)
+    lo, hi = int(bounds[rank]), int(bounds[rank + 1])
+    n_local = hi - lo
+    b_t = torch.as_tensor(bounds, device=dev)
+    cols = cols.to(torch.int64)
+    # rows finished by each tile range of every rank's hop (a function of that rank's row pointer alone)
+    mine = chunk_row_bounds(loc_ptr.detach().cpu().numpy(), C)
+    crb_all = [None] * world
+    dist.all_gather_object(crb_all, [int(v) for v in mine], group=group)
+    crb = [torch.as_tensor(np.asarray(c, dtype=np.int64), device=dev) for c in crb_all]
+    # receive side: the distinct remote rows this rank references, sorted by global id (= by owner, then local id)
+    owner = torch.searchsorted(b_t, cols, right=True) - 1
+    remote = owner != rank
+    uniq = torch.unique(cols[remote])
+    u_owner = torch.searchsorted(b_t, uniq, right=True) - 1
+    per_peer = torch.bincount(u_owner, minlength=world)                     # rows referenced per owner
+    peer_first = torch.cumsum(per_peer, 0) - per_peer                       # start of each owner's block in uniq
+    u_local = uniq - b_t[u_owner]                                           # id inside the owner's shard
+    # chunk of the owner's hop that finishes each referenced row
+    u_chunk = torch.zeros_like(uniq)
+    for q in range(world):
+        m = u_owner == q
+        if q != rank and bool(m.any()):
+            u_chunk[m] = torch.searchsorted(crb[q], u_local[m], right=True) - 1
+    # layout: chunk-major, then owner, then row
+    counts = torch.zeros((C, world), dtype=torch.int64, device=dev)
+    if uniq.numel():
+        counts.view(-1).index_add_(0, u_chunk * world + u_owner, torch.ones_like(uniq))
+    seg_start = (torch.cumsum(counts.view(-1), 0) - counts.view(-1)).view(C, world)
+    # position of every referenced row inside its (chunk, owner) block: rows of one owner are sorted, chunks are
+    # consecutive ranges of them, so the rank inside the block is the index in uniq minus the block's first index
+    idx_in_uniq = torch.arange(uniq.numel(), device=dev)
+    first_of_block = torch.zeros((C, world), dtype=torch.int64, device=dev)
+    blk = u_chunk * world + u_owner
+    if uniq.numel():
+        first_of_block.view(-1).scatter_reduce_(0, blk, idx_in_uniq, reduce="amin", include_self=False)
+    pos_u = n_local + seg_start.view(-1)[blk] + (idx_in_uniq - first_of_block.view(-1)[blk])
+    new_cols = torch.empty_like(cols)
+    new_cols[~remote] = cols[~remote] - lo
+    if bool(remote.any()):
+        new_cols[remote] = pos_u[torch.searchsorted(uniq, cols[remote])]
+    recv_counts = counts.cpu().numpy().tolist()
+    n_halo = int(counts.sum())
+    # send side: every owner learns which of its rows each peer references (one all-to-all of the lists)
+    send_counts_t = per_peer.clone()
+    send_counts_t[rank] = 0
+    got_counts = torch.empty_like(send_counts_t)
+    dist.all_to_all_single(got_counts, send_counts_t, group=group)
+    out_list = u_local                                                      # already grouped by owner, sorted
+    in_list = torch.empty(int(got_counts.sum()), dtype=torch.int64, device=dev)
+    dist.all_to_all_single(in_list, out_list, output_split_sizes=got_counts.cpu().tolist(),
+                           input_split_sizes=send_counts_t.cpu().tolist(), group=group)
+    send_rows = [[np.zeros(0, dtype=np.int64) for _ in range(world)] for _ in range(C)]
+    starts = (torch.cumsum(got_counts, 0) - got_counts).cpu().tolist()
+    my_crb = crb[rank]
+    for p in range(world):
+        if p == rank or int(got_counts[p]) == 0:
+            continue
+        theirs = in_list[starts[p]:starts[p] + int(got_counts[p])]
+        cut = torch.searchsorted(theirs, my_crb).cpu().tolist()
+        host = theirs.cpu().numpy()
+        for c in range(C):
+            send_rows[c][p] = host[cut[c]:cut[c + 1]]
+    return RankPlan(rank, world, bounds, loc_ptr.to(torch.int64), new_cols.to(torch.int32), vals.to(torch.float32),
+                    n_local + n_halo, "halo", C, send_rows, recv_counts, mine, 0)
+
+
 # ---------------------------------------------------------------------------------------------------------------
 # NVLink peer memory (CUDA IPC) for the NCCL-free halo exchange
 # ---------------------------------------------------------------------------------------------------------------

@@ -146,3 +146,35 @@ def test_chunk_row_bounds_against_item_walk():
                 want = [0] + [_brute_force_rows_before(indptr, min((n_tiles * c // n_chunks) * tile_items, total))
                               for c in range(1, n_chunks)] + [n]
                 assert list(got) == want, (trial, tile_items, n_chunks)
+
+
+def _collective_worker(rank, world, port, chunks, out_dir):
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        from sgl_b200.dist import build_plan_collective
+        a = _graph(7, n=900, m=9000)
+        bounds = partition_rows(a.indptr, world)
+        lo, hi = int(bounds[rank]), int(bounds[rank + 1])
+        loc_ptr = torch.from_numpy(a.indptr[lo:hi + 1] - a.indptr[lo])
+        cols = torch.from_numpy(a.indices[a.indptr[lo]:a.indptr[hi]].astype(np.int64))
+        vals = torch.from_numpy(a.data[a.indptr[lo]:a.indptr[hi]].astype(np.float32))
+        got = build_plan_collective(loc_ptr, cols, vals, bounds, n_chunks=chunks)
+        want = build_plan(a.indptr, a.indices, a.data, a.shape[1], world, rank, "halo", n_chunks=chunks)
+        ok = (np.array_equal(got.indices.numpy(), want.indices) and got.n_ext == want.n_ext
+              and got.recv_counts == want.recv_counts and list(got.chunk_rows) == list(want.chunk_rows)
+              and all(np.array_equal(got.send_rows[c][q], want.send_rows[c][q])
+                      for c in range(chunks) for q in range(world)))
+        np.save(os.path.join(out_dir, f"ok_{rank}.npy"), np.array([ok]))
+    finally:
+        dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("world,chunks", [(2, 1), (3, 4)])
+def test_collective_plan_equals_full_matrix_plan(tmp_path, world, chunks):
+    """Each rank sees only its own rows; the collectively built plan must equal the one derived from the full matrix."""
+    port = _free_port()
+    mp.spawn(_collective_worker, args=(world, port, chunks, str(tmp_path)), nprocs=world, join=True)
+    for r in range(world):
+        assert bool(np.load(tmp_path / f"ok_{r}.npy")[0]), f"rank {r}"

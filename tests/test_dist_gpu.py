@@ -29,7 +29,16 @@ def _worker(rank, world, port, mode, tmp, chunks=1, transport="peer"):
                              (np.concatenate([rows, cols]), np.concatenate([cols, rows]))), shape=(n, n))
         a = O.laplacian_adj(adj, 0.5)
         x = rng.standard_normal((n, d)).astype(np.float32)
-        plan = build_plan(a.indptr, a.indices, a.data, n, world, rank, mode, n_chunks=chunks)
+        if mode == "halo" and chunks == 4:      # plan built collectively from this rank's rows only (device tensors)
+            from sgl_b200.dist import build_plan_collective, partition_rows
+            bounds = partition_rows(a.indptr, world)
+            b0, b1 = int(bounds[rank]), int(bounds[rank + 1])
+            j0, j1 = int(a.indptr[b0]), int(a.indptr[b1])
+            plan = build_plan_collective(torch.from_numpy(a.indptr[b0:b1 + 1] - a.indptr[b0]).cuda(),
+                                         torch.from_numpy(a.indices[j0:j1].astype(np.int64)).cuda(),
+                                         torch.from_numpy(a.data[j0:j1].astype(np.float32)).cuda(), bounds, n_chunks=chunks)
+        else:
+            plan = build_plan(a.indptr, a.indices, a.data, n, world, rank, mode, n_chunks=chunks)
         op = DistOperator(plan, mode="exact")
         lo, hi = plan.bounds[rank], plan.bounds[rank + 1]
         hops = op.propagate(torch.from_numpy(x[lo:hi]).cuda(), K)
