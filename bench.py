@@ -56,6 +56,9 @@ def parse_args():
     ap.add_argument("--exchange", default="halo", choices=["halo", "allgather"])
     ap.add_argument("--transport", default="peer", choices=["peer", "nccl"],
                     help="halo rows move by our NVLink peer-store kernels (CUDA IPC) or by NCCL all_to_all")
+    ap.add_argument("--partition", default="row", choices=["row", "feature"],
+                    help="N>1: 1-D row partition with a halo exchange per hop (default, SURVEY 8e), or A^ replicated and the "
+                         "feature columns split across GPUs (no per-hop exchange; one all-gather of the last hop)")
     ap.add_argument("--plan", default="replicated", choices=["replicated", "collective"],
                     help="halo plan from the full matrix on every rank (numpy) or built collectively from local rows (torch)")
     ap.add_argument("--chunks", type=int, default=4, help="row chunks the hop is pipelined over against its halo exchange")
@@ -462,6 +465,8 @@ def run_dist(args):
     dist.init_process_group("nccl", device_id=dev)
     name = args.workload or "arxiv"
     rows, cols, n, d, K = device_graph(name, dev)
+    if args.partition == "feature":
+        return run_feature_split(args, rank, world, local, dev, name, rows, cols, n, d, K)
     t0 = time.perf_counter()
     parts = normalized_adjacency_device(rows, cols, n, None, r=0.5, alpha=None, pow_on="host")
     del rows, cols
@@ -572,6 +577,55 @@ def run_dist(args):
                 "cpu_baseline": None,
                 "e2e": e2e, "clocks": clocks, "gpu_launches": args.steps * K * 3,
                 "setup": {"build_plan_s": t_build}}
+        print(json.dumps(line))
+    dist.destroy_process_group()
+
+
+def run_feature_split(args, rank, world, local, dev, name, rows, cols, n, d, K):
+    """N > 1, alternative partition: every GPU holds all of A^ and propagates d / N feature columns; the only collective
+    is one all-gather of the last hop's column blocks inside the timed step."""
+    import torch
+    import torch.distributed as dist
+    from sgl_b200.dist import FeatureSplitOperator
+    from sgl_b200.graph_build import build_operator_device
+
+    t0 = time.perf_counter()
+    op = build_operator_device(rows, cols, n, r=0.5)
+    nnz = int(op.nnz)
+    op.parts = None
+    t_build = time.perf_counter() - t0
+    fs = FeatureSplitOperator(world=world, rank=rank, operator=op, mode=args.mode)
+    cb = fs.column_bounds(d, world)
+    x_full = torch.randn(n, d, generator=torch.Generator().manual_seed(0))
+    x_blk = x_full[:, int(cb[rank]):int(cb[rank + 1])].contiguous().to(dev)
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
+
+    def step():
+        return fs.gather_columns(fs.propagate(x_blk, K)[-1], d)
+
+    for _ in range(max(args.warmup, 3)):
+        step()
+    torch.cuda.synchronize()
+    dist.barrier()
+    starts = [torch.cuda.Event(enable_timing=True) for _ in range(args.steps)]
+    stops = [torch.cuda.Event(enable_timing=True) for _ in range(args.steps)]
+    for i in range(args.steps):
+        flush.fill_(i & 0xFF)
+        starts[i].record()
+        step()
+        stops[i].record()
+    torch.cuda.synchronize()
+    dist.barrier()
+    mine = torch.tensor([sum(s.elapsed_time(e) for s, e in zip(starts, stops)) / 1e3], device=dev, dtype=torch.float64)
+    dist.all_reduce(mine, op=dist.ReduceOp.MAX)
+    total_s = float(mine.item())
+    if rank == 0:
+        line = {"metric": METRIC, "value": nnz * K * args.steps / total_s, "unit": UNIT, "n_gpus": world,
+                "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": 1e3 * total_s / args.steps,
+                "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+                "config": dict(workload_config(name, n, nnz, d, K, args), partition=f"feature split x{world} (A^ replicated)"),
+                "roofline": None, "cpu_baseline": None, "e2e": None, "clocks": None, "gpu_launches": args.steps * K,
+                "setup": {"build_on_device_s": t_build}}
         print(json.dumps(line))
     dist.destroy_process_group()
 

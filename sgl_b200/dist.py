@@ -588,6 +588,60 @@ class DistOperator:
             self._op.close()
 
 
+class FeatureSplitOperator:
+    """The zero-communication alternative of SURVEY.md section 8(e): A^ is replicated on every GPU (17 GB even for the
+    2-billion-edge config) and the FEATURE dimension is split, rank p propagating columns [c_p, c_{p+1}) of X.  Column
+    blocks of A^^k X are independent, so the K hops need no exchange at all; one all-gather at the end assembles the
+    rows (or the caller keeps the column blocks).  Kept next to the row partition as the measured comparison -- it
+    trades a per-hop halo exchange for gathers of narrow rows (d / world floats each).
+
+    `local_hop(x_block, out)` computes out = A^ @ x_block; default: the CUDA kernel through CsrOperator."""
+
+    def __init__(self, adj_norm=None, world: int = 1, rank: int = 0, group=None, local_hop: Optional[Callable] = None,
+                 operator=None, mode: str = "fast"):
+        self.world, self.rank, self.group, self.mode = world, rank, group, mode
+        if local_hop is None:
+            from .runtime import CsrOperator, require_cuda
+            require_cuda()
+            self._op = operator if operator is not None else CsrOperator.from_scipy(adj_norm)
+            self._hop = lambda x, out: self._op.spmm(x, out=out, mode=self.mode)
+        else:
+            self._op = None
+            self._hop = local_hop
+
+    @staticmethod
+    def column_bounds(d: int, world: int, align: int = 4) -> np.ndarray:
+        """Contiguous column blocks, multiples of `align` floats (16-byte rows) wherever d allows."""
+        units = (d + align - 1) // align
+        cuts = [min(d, align * ((units * p) // world)) for p in range(world)] + [d]
+        return np.asarray(cuts, dtype=np.int64)
+
+    def propagate(self, x_block: torch.Tensor, prop_steps: int) -> List[torch.Tensor]:
+        """K hops of this rank's column block: [X[:, blk], (A^X)[:, blk], ...] -- no communication."""
+        hops = [x_block.contiguous()]
+        for _ in range(prop_steps):
+            out = torch.empty_like(hops[-1])
+            self._hop(hops[-1], out)
+            hops.append(out)
+        return hops
+
+    def gather_columns(self, block: torch.Tensor, d: int) -> torch.Tensor:
+        """Assemble the full [N, d] matrix of one hop from every rank's column block (one all-gather, not per hop)."""
+        if self.world == 1:
+            return block
+        bounds = self.column_bounds(d, self.world)
+        width = int(np.max(np.diff(bounds)))
+        padded = block.new_zeros((block.shape[0], width))
+        padded[:, :block.shape[1]] = block
+        parts = [torch.empty_like(padded) for _ in range(self.world)]
+        dist.all_gather(parts, padded, group=self.group)
+        return torch.cat([parts[q][:, :int(bounds[q + 1] - bounds[q])] for q in range(self.world)], dim=1)
+
+    def close(self):
+        if self._op is not None:
+            self._op.close()
+
+
 def exchange_volume_bytes(plan: RankPlan, d: int) -> int:
     """Bytes this rank RECEIVES per hop."""
     if plan.mode == "allgather":

@@ -178,3 +178,39 @@ def test_collective_plan_equals_full_matrix_plan(tmp_path, world, chunks):
     mp.spawn(_collective_worker, args=(world, port, chunks, str(tmp_path)), nprocs=world, join=True)
     for r in range(world):
         assert bool(np.load(tmp_path / f"ok_{r}.npy")[0]), f"rank {r}"
+
+
+def _feature_split_worker(rank, world, port, d, K, out_dir):
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        from sgl_b200.dist import FeatureSplitOperator
+        a = _graph(9)
+        x = np.random.default_rng(10).standard_normal((a.shape[0], d)).astype(np.float32)
+
+        def oracle_hop(xb, out):
+            out.copy_(torch.from_numpy(O.spmm_hop(a, xb.numpy(), "fma")))
+
+        op = FeatureSplitOperator(world=world, rank=rank, local_hop=oracle_hop)
+        cb = op.column_bounds(d, world)
+        hops = op.propagate(torch.from_numpy(x[:, cb[rank]:cb[rank + 1]].copy()), K)
+        full = op.gather_columns(hops[-1], d)
+        np.save(os.path.join(out_dir, f"fs_{rank}.npy"), full.numpy())
+    finally:
+        dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("world,d", [(2, 12), (3, 10)])
+def test_feature_split_needs_no_exchange_and_matches(tmp_path, world, d):
+    from sgl_b200.dist import FeatureSplitOperator
+    cb = FeatureSplitOperator.column_bounds(d, world)
+    assert cb[0] == 0 and cb[-1] == d and np.all(np.diff(cb) >= 0)
+    K = 3
+    port = _free_port()
+    mp.spawn(_feature_split_worker, args=(world, port, d, K, str(tmp_path)), nprocs=world, join=True)
+    a = _graph(9)
+    x = np.random.default_rng(10).standard_normal((a.shape[0], d)).astype(np.float32)
+    ref = O.propagate(a, x, K, "fma")[-1]
+    for r in range(world):
+        assert np.array_equal(np.load(tmp_path / f"fs_{r}.npy"), ref)   # column blocks are independent: bit-exact
