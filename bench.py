@@ -61,6 +61,8 @@ def parse_args():
                          "feature columns split across GPUs (no per-hop exchange; one all-gather of the last hop)")
     ap.add_argument("--plan", default="replicated", choices=["replicated", "collective"],
                     help="halo plan from the full matrix on every rank (numpy) or built collectively from local rows (torch)")
+    ap.add_argument("--relabel", default="none", choices=["none", "degree"],
+                    help="experiment: relabel the vertices by descending degree before building A^")
     ap.add_argument("--chunks", type=int, default=4, help="row chunks the hop is pipelined over against its halo exchange")
     return ap.parse_args()
 
@@ -248,6 +250,13 @@ def run_b200(args):
     from sgl_b200.graph_build import build_operator_device, parts_to_scipy
     t0 = time.perf_counter()
     rows, cols, n, d, K = device_graph(name, dev)
+    if args.relabel == "degree":
+        deg = torch.bincount(rows, minlength=n)
+        order = torch.argsort(deg, descending=True, stable=True)
+        newid = torch.empty_like(order)
+        newid[order] = torch.arange(n, device=dev)
+        rows, cols = newid[rows], newid[cols]
+        del deg, order, newid
     torch.cuda.synchronize()
     t_gen = time.perf_counter() - t0
     # A^ = D^-1/2 (A+I)^T D^-1/2 built on the device (sgl_b200.graph_build: bit-identical structure and values to the

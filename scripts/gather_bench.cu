@@ -3,8 +3,10 @@
 //   ldg     : LDG.128 into registers, U rows in flight per warp
 //   ldgsts  : cp.async (LDGSTS.128) into a per-warp shared-memory ring, consumed with LDS.128
 //   bulk    : cp.async.bulk (TMA 1-D bulk copy, UBLKCP), one 512 B row per LANE per instruction, mbarrier completion
+//   gather4 : cp.async.bulk.tensor.2d.tile::gather4 (UTMALDG, sm_100): FOUR rows of a 2-D tensor map per instruction
 // Build:  nvcc -gencode arch=compute_100a,code=sm_100a -O3 -lineinfo -o gather_bench scripts/gather_bench.cu
 // Run  :  ./gather_bench [n_rows] [n_idx] [skew 0|1]
+#include <cuda.h>
 #include <cuda_runtime.h>
 #include <stdint.h>
 #include <stdio.h>
@@ -154,6 +156,68 @@ __global__ void __launch_bounds__(WARPS * 32) gather_bulk(const float *__restric
     reinterpret_cast<float4 *>(out + w * D)[lane] = acc;
 }
 
+// ---------------------------------------------------------------------------------------------------------------
+// per-warp ring filled by TMA gather4: lanes 0..ISSUERS-1 each fetch FOUR 512 B rows per instruction through a 2-D tensor
+// map of X (box = {D, 1}); ROWS = 4 * ISSUERS rows per stage
+template <int STAGES, int ISSUERS, int WARPS>
+__global__ void __launch_bounds__(WARPS * 32) gather_g4(const __grid_constant__ CUtensorMap tmap, const int *__restrict__ idx,
+                                                        int64_t per_warp, float *__restrict__ out)
+{
+    constexpr int ROWS = 4 * ISSUERS;
+    extern __shared__ __align__(128) unsigned char smem[];
+    const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
+    const int64_t w = (int64_t)blockIdx.x * WARPS + wib;
+    const int *my = idx + w * per_warp;
+    float *ring = reinterpret_cast<float *>(smem) + (size_t)wib * STAGES * ROWS * D;
+    uint64_t *bars = reinterpret_cast<uint64_t *>(smem + (size_t)WARPS * STAGES * ROWS * D * 4) + wib * STAGES;
+    if (lane == 0) {
+        for (int s = 0; s < STAGES; ++s)
+            asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(smem_u32(bars + s)));
+        asm volatile("fence.mbarrier_init.release.cluster;");
+    }
+    __syncwarp();
+    float4 acc = make_float4(0, 0, 0, 0);
+    const int64_t n_groups = per_warp / ROWS;
+    auto issue = [&](int64_t g) {
+        const int stage = (int)(g % STAGES);
+        const uint32_t bar = smem_u32(bars + stage);
+        if (lane == 0)
+            asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(ROWS * D * 4));
+        __syncwarp();
+        if (lane < ISSUERS) {
+            const int4 c = *reinterpret_cast<const int4 *>(my + g * ROWS + lane * 4);
+            const uint32_t dst = smem_u32(ring + ((size_t)stage * ROWS + lane * 4) * D);
+            asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.tile::gather4.mbarrier::complete_tx::bytes"
+                         " [%0], [%1, {%3, %4, %5, %6, %7}], [%2];" ::"r"(dst), "l"(&tmap), "r"(bar), "r"(0), "r"(c.x),
+                         "r"(c.y), "r"(c.z), "r"(c.w)
+                         : "memory");
+        }
+    };
+    for (int s = 0; s < STAGES - 1 && s < n_groups; ++s) issue(s);
+#pragma unroll 1
+    for (int64_t g = 0; g < n_groups; ++g) {
+        if (g + STAGES - 1 < n_groups) issue(g + STAGES - 1);
+        const int stage = (int)(g % STAGES);
+        const uint32_t bar = smem_u32(bars + stage);
+        const uint32_t parity = (uint32_t)((g / STAGES) & 1);
+        uint32_t done = 0;
+        while (!done) {
+            asm volatile("{ .reg .pred p; mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2; selp.u32 %0, 1, 0, p; }"
+                         : "=r"(done)
+                         : "r"(bar), "r"(parity)
+                         : "memory");
+        }
+        const float4 *rows = reinterpret_cast<const float4 *>(ring + (size_t)stage * ROWS * D);
+#pragma unroll 4
+        for (int r = 0; r < ROWS; ++r) {
+            const float4 v = rows[r * (D / 4) + lane];
+            acc.x += v.x; acc.y += v.y; acc.z += v.z; acc.w += v.w;
+        }
+        __syncwarp();
+    }
+    reinterpret_cast<float4 *>(out + w * D)[lane] = acc;
+}
+
 __global__ void stream_read(const float4 *__restrict__ X, int64_t n4, float *out)
 {
     float4 acc = make_float4(0, 0, 0, 0);
@@ -260,5 +324,40 @@ int main(int argc, char **argv)
     RUN_BULK(3, 4, 512)
     RUN_BULK(2, 4, 128)
     RUN_BULK(2, 4, 2048)
+    {
+        // 2-D tensor map of X: inner dim D floats, outer dim n_rows, box {D, 1} (gather4 fetches 4 such boxes)
+        typedef CUresult (*EncodeFn)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *, const cuuint64_t *, const cuuint64_t *,
+                                     const cuuint32_t *, const cuuint32_t *, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                     CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+        void *fn = nullptr;
+        cudaDriverEntryPointQueryResult qres;
+        CK(cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &qres));
+        CUtensorMap tmap;
+        cuuint64_t dims[2] = {(cuuint64_t)D, (cuuint64_t)n_rows};
+        cuuint64_t strides[1] = {(cuuint64_t)D * 4};
+        cuuint32_t box[2] = {(cuuint32_t)D, 1};
+        cuuint32_t estr[2] = {1, 1};
+        CUresult r = ((EncodeFn)fn)(&tmap, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, X, dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                                    CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_NONE, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+        if (r != CUDA_SUCCESS) { printf("cuTensorMapEncodeTiled failed: %d\n", (int)r); return 1; }
+#define RUN_G4(STAGES, ISSUERS, WARPS, PW)                                                            \
+    {                                                                                                 \
+        const int64_t warps = n_idx / (PW);                                                           \
+        const size_t sm = (size_t)WARPS * STAGES * 4 * ISSUERS * D * 4 + WARPS * STAGES * 8;          \
+        CK(cudaFuncSetAttribute(gather_g4<STAGES, ISSUERS, WARPS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm)); \
+        float ms = time_ms([&] { gather_g4<STAGES, ISSUERS, WARPS><<<(unsigned)(warps / WARPS), WARPS * 32, sm>>>(tmap, idx, PW, out); }); \
+        printf("gather4 stages=%d rows/stage=%-2d warps/cta=%d smem=%3zuKB per_warp=%-5d %8.3f ms  %8.1f GB/s\n", STAGES, 4 * ISSUERS, WARPS, sm >> 10, PW, ms, bytes / ms / 1e6); \
+    }
+        RUN_G4(2, 8, 4, 512)
+        RUN_G4(2, 8, 2, 512)
+        RUN_G4(3, 8, 2, 512)
+        RUN_G4(2, 4, 4, 512)
+        RUN_G4(3, 4, 4, 512)
+        RUN_G4(4, 2, 4, 512)
+        RUN_G4(4, 2, 8, 512)
+        RUN_G4(2, 2, 8, 512)
+        RUN_G4(3, 1, 8, 512)
+        RUN_G4(6, 1, 8, 512)
+    }
     return 0;
 }

@@ -50,6 +50,10 @@ struct SpmmParams {
     float *carry_ws;
     int64_t ws_ld;
     int stream_y;  // 1: output rows are stored with the streaming (evict-first) policy
+    // L2 residency control for gathered rows: columns below hub_cols are loaded with an evict_last policy, the
+    // rest with cold_policy (0 = no hint, 1 = evict_first); hub_cols == 0 disables the hints
+    uint32_t hub_cols;
+    int cold_policy;
     // in-kernel fold of cut rows (fold != 0): every tile that holds a piece of a cut row stores its partial in the
     // workspace and arrives on the row's counter; the LAST arriver adds the partials in tile order and writes Y
     int fold;
@@ -115,6 +119,11 @@ template <> struct Slice<4> {
     __device__ __forceinline__ void load_nc(const char *p) { v = __ldg(reinterpret_cast<const ulonglong2 *>(p)); }
     __device__ __forceinline__ void load(const char *p) { v = *reinterpret_cast<const ulonglong2 *>(p); }
     __device__ __forceinline__ void load_l2(const char *p) { v = __ldcg(reinterpret_cast<const ulonglong2 *>(p)); }
+    __device__ __forceinline__ void load_hint(const char *p, uint64_t pol)
+    {
+        asm volatile("ld.global.nc.L1::no_allocate.L2::cache_hint.v2.u64 {%0, %1}, [%2], %3;"
+                     : "=l"(v.x), "=l"(v.y) : "l"(p), "l"(pol));
+    }
     __device__ __forceinline__ void add(const Slice &x)
     {
         asm("add.rn.f32x2 %0, %0, %2; add.rn.f32x2 %1, %1, %3;" : "+l"(v.x), "+l"(v.y) : "l"(x.v.x), "l"(x.v.y));
@@ -137,6 +146,10 @@ template <> struct Slice<2> {
     __device__ __forceinline__ void load_nc(const char *p) { v = __ldg(reinterpret_cast<const unsigned long long *>(p)); }
     __device__ __forceinline__ void load(const char *p) { v = *reinterpret_cast<const unsigned long long *>(p); }
     __device__ __forceinline__ void load_l2(const char *p) { v = __ldcg(reinterpret_cast<const unsigned long long *>(p)); }
+    __device__ __forceinline__ void load_hint(const char *p, uint64_t pol)
+    {
+        asm volatile("ld.global.nc.L1::no_allocate.L2::cache_hint.u64 %0, [%1], %2;" : "=l"(v) : "l"(p), "l"(pol));
+    }
     __device__ __forceinline__ void add(const Slice &x) { asm("add.rn.f32x2 %0, %0, %1;" : "+l"(v) : "l"(x.v)); }
     __device__ __forceinline__ void store(char *p) const { *reinterpret_cast<unsigned long long *>(p) = v; }
     __device__ __forceinline__ void store_streaming(char *p) const
@@ -154,6 +167,10 @@ template <> struct Slice<1> {
     __device__ __forceinline__ void load_nc(const char *p) { v = __ldg(reinterpret_cast<const float *>(p)); }
     __device__ __forceinline__ void load(const char *p) { v = *reinterpret_cast<const float *>(p); }
     __device__ __forceinline__ void load_l2(const char *p) { v = __ldcg(reinterpret_cast<const float *>(p)); }
+    __device__ __forceinline__ void load_hint(const char *p, uint64_t pol)
+    {
+        asm volatile("ld.global.nc.L1::no_allocate.L2::cache_hint.f32 %0, [%1], %2;" : "=f"(v) : "l"(p), "l"(pol));
+    }
     __device__ __forceinline__ void add(const Slice &x) { v = __fadd_rn(v, x.v); }
     __device__ __forceinline__ void store(char *p) const { *reinterpret_cast<float *>(p) = v; }
     __device__ __forceinline__ void store_streaming(char *p) const
@@ -163,7 +180,7 @@ template <> struct Slice<1> {
     __device__ __forceinline__ void fma(float w, const Slice &x) { v = fmaf(w, x.v, v); }
 };
 
-template <int VEC, int VPL, int U, bool ACCUM, int MINB, int PIPE>
+template <int VEC, int VPL, int U, bool ACCUM, int MINB, int PIPE, bool HINT = false>
 __global__ void __launch_bounds__(kWarpsPerBlock * 32, MINB) spmm_flat_kernel(const SpmmParams p)
 {
     static_assert(32 % U == 0, "U must divide the batch of 32 non-zeros");
@@ -252,6 +269,13 @@ __global__ void __launch_bounds__(kWarpsPerBlock * 32, MINB) spmm_flat_kernel(co
 
     const int32_t *cols = p.indices + j0;
     const float *vals = p.vals + j0;
+    uint64_t pol_hub = 0, pol_cold = 0;
+    if constexpr (HINT) {
+        asm volatile("createpolicy.fractional.L2::evict_last.b64 %0, 1.0;" : "=l"(pol_hub));
+        if (p.cold_policy == 1) asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(pol_cold));
+        else asm volatile("createpolicy.fractional.L2::evict_normal.b64 %0, 1.0;" : "=l"(pol_cold));
+    }
+    const uint32_t hub_cols = p.hub_cols;
 
     // (col, val) of the next 32 non-zeros are fetched into registers one batch ahead of their publication
     int32_t col_next = 0;
@@ -284,7 +308,14 @@ __global__ void __launch_bounds__(kWarpsPerBlock * 32, MINB) spmm_flat_kernel(co
         for (int u = 0; u < U; ++u) {
             const uint32_t c = (uint32_t)pp[u].x;
 #pragma unroll
-            for (int v = 0; v < VPL; ++v) buf[u][v].load_nc(xbase[v] + (uint64_t)c * ldx_bytes);
+            if constexpr (HINT) {
+                const uint64_t pol = c < hub_cols ? pol_hub : pol_cold;
+#pragma unroll
+                for (int v = 0; v < VPL; ++v) buf[u][v].load_hint(xbase[v] + (uint64_t)c * ldx_bytes, pol);
+            } else {
+#pragma unroll
+                for (int v = 0; v < VPL; ++v) buf[u][v].load_nc(xbase[v] + (uint64_t)c * ldx_bytes);
+            }
         }
     };
     auto consume = [&](Slice<VEC> (&buf)[U][VPL], int g) {
@@ -608,9 +639,50 @@ __global__ void __launch_bounds__(kWarpsPerBlock * 32)
     }
 }
 
+static int env_int(const char *name, int dflt)
+{
+    const char *e = getenv(name);
+    return e ? atoi(e) : dflt;
+}
+
+template <typename Kern>
+static cudaError_t launch_windowed(Kern kern, const SpmmParams &p, dim3 grid, cudaStream_t stream)
+{
+    // experiment: pin the first window_mb MB of X in L2 through a per-launch access policy window
+    static int window_mb = env_int("SGLB200_L2_WINDOW_MB", 0);
+    if (window_mb <= 0) {
+        kern<<<grid, kWarpsPerBlock * 32, 0, stream>>>(p);
+        return cudaGetLastError();
+    }
+    static bool limit_set = false;
+    if (!limit_set) {
+        cudaDeviceSetLimit(cudaLimitPersistingL2CacheSize, (size_t)window_mb << 20);
+        limit_set = true;
+    }
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = grid;
+    cfg.blockDim = dim3(kWarpsPerBlock * 32);
+    cfg.stream = stream;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeAccessPolicyWindow;
+    attr[0].val.accessPolicyWindow.base_ptr = const_cast<float *>(p.X);
+    attr[0].val.accessPolicyWindow.num_bytes = (size_t)window_mb << 20;
+    attr[0].val.accessPolicyWindow.hitRatio = 1.0f;
+    attr[0].val.accessPolicyWindow.hitProp = cudaAccessPropertyPersisting;
+    attr[0].val.accessPolicyWindow.missProp = cudaAccessPropertyStreaming;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+    return cudaLaunchKernelEx(&cfg, kern, p);
+}
+
 template <int VEC, int VPL, int U, int MINB, int PIPE = 1>
 static cudaError_t launch_flat(const SpmmParams &p, bool accum, dim3 grid, cudaStream_t stream)
 {
+    if (!accum && p.hub_cols > 0) {
+        spmm_flat_kernel<VEC, VPL, U, false, MINB, PIPE, true><<<grid, kWarpsPerBlock * 32, 0, stream>>>(p);
+        return cudaGetLastError();
+    }
+    if (!accum) return launch_windowed(spmm_flat_kernel<VEC, VPL, U, false, MINB, PIPE>, p, grid, stream);
     if (accum) spmm_flat_kernel<VEC, VPL, U, true, (MINB > 3 ? 3 : MINB), 1><<<grid, kWarpsPerBlock * 32, 0, stream>>>(p);
     else spmm_flat_kernel<VEC, VPL, U, false, MINB, PIPE><<<grid, kWarpsPerBlock * 32, 0, stream>>>(p);
     return cudaGetLastError();
@@ -687,6 +759,18 @@ int spmm_launch_tiles(sglb200_graph *g, const float *X, int64_t ldx, float *Y, i
         s = &g->exact;
     }
     if (s->n_tiles == 0) return SGLB200_OK;
+    {
+        // experiment: column tiling -- the hop runs once per block of col_tile feature columns so that the hub rows
+        // of one block (col_tile * 4 bytes each) fit L2 in larger numbers
+        static int col_tile = env_int("SGLB200_COL_TILE", 0);
+        if (col_tile > 0 && d > col_tile && d % col_tile == 0 && !accumulate) {
+            for (int c0 = 0; c0 < d; c0 += col_tile) {
+                const int st = spmm_launch_tiles(g, X + c0, ldx, Y + c0, ldy, col_tile, mode, 0, tile_begin, tile_end, stream);
+                if (st != SGLB200_OK) return st;
+            }
+            return SGLB200_OK;
+        }
+    }
     if (tile_end < 0 || tile_end > s->n_tiles) tile_end = s->n_tiles;
     if (tile_begin < 0) tile_begin = 0;
     if (tile_begin >= tile_end) return SGLB200_OK;
@@ -744,6 +828,12 @@ int spmm_launch_tiles(sglb200_graph *g, const float *X, int64_t ldx, float *Y, i
             force = e ? atoi(e) : -1;
         }
         p.stream_y = force >= 0 ? force : 1;
+    }
+    {
+        static int hub = env_int("SGLB200_HUB_COLS", 0);
+        static int cold = env_int("SGLB200_COLD_POLICY", 1);
+        p.hub_cols = (uint32_t)hub;
+        p.cold_policy = cold;
     }
 
     const dim3 grid((unsigned)((tile_end - tile_begin + kWarpsPerBlock - 1) / kWarpsPerBlock), (unsigned)col_blocks, 1);
