@@ -61,6 +61,7 @@ def parse_args():
                          "feature columns split across GPUs (no per-hop exchange; one all-gather of the last hop)")
     ap.add_argument("--plan", default="replicated", choices=["replicated", "collective"],
                     help="halo plan from the full matrix on every rank (numpy) or built collectively from local rows (torch)")
+    ap.add_argument("--feat-dim", type=int, default=0, help="experiment: override the feature width of the workload")
     ap.add_argument("--relabel", default="none", choices=["none", "degree"],
                     help="experiment: relabel the vertices by descending degree before building A^")
     ap.add_argument("--chunks", type=int, default=4, help="row chunks the hop is pipelined over against its halo exchange")
@@ -250,6 +251,8 @@ def run_b200(args):
     from sgl_b200.graph_build import build_operator_device, parts_to_scipy
     t0 = time.perf_counter()
     rows, cols, n, d, K = device_graph(name, dev)
+    if args.feat_dim > 0:
+        d = args.feat_dim
     if args.relabel == "degree":
         deg = torch.bincount(rows, minlength=n)
         order = torch.argsort(deg, descending=True, stable=True)

@@ -62,7 +62,8 @@ enum sglb200_agg {
     SGLB200_AGG_MIN = 3,      /* min_message_op.py:11-12                                                 */
     SGLB200_AGG_WEIGHTED = 4, /* simple_weighted_message_op.py:40-56 + utils.py:91-102  acc += y_k * w_k */
     SGLB200_AGG_CONCAT = 5,   /* concat_message_op.py:11-12  hstack into [N, n_feats*d]                  */
-    SGLB200_AGG_OSD = 6       /* over_smooth_distance_op.py:11-33  NAFS cosine-softmax hop weights       */
+    SGLB200_AGG_OSD = 6,      /* over_smooth_distance_op.py:11-33  NAFS cosine-softmax hop weights       */
+    SGLB200_AGG_LAST = 7      /* last_message_op.py:9-10  the last hop (sglb200_propagate_fused only)    */
 };
 
 typedef struct sglb200_graph *sglb200_graph_t;
@@ -113,7 +114,11 @@ SGLB200_API int sglb200_spmm(sglb200_graph_t g, const float *X, int64_t ldx, flo
 /* chunked hop for pipelining a hop against the halo exchange of a row partition:
  * sglb200_graph_chunks splits the warp schedule of `mode` into n_chunks consecutive tile ranges and reports, per
  * chunk, the tile bounds and the rows whose final value that chunk produces (row_bounds[c] .. row_bounds[c+1]-1);
- * sglb200_spmm_tiles runs one such range (cut rows that finish inside it are folded before it returns to the stream). */
+ * sglb200_spmm_tiles runs one such range (cut rows that finish inside it are folded before it returns to the stream).
+ * Cut rows are folded by per-row arrival counters kept in the handle, so the ranges of ONE hop must be issued
+ * completely, in ascending order, on one stream; an out-of-order range is rejected (SGLB200_ERR_INVALID), a hop that
+ * starts at tile 0 while an earlier hop was left unfinished starts from fresh counters, and a hop issued on a
+ * different stream than the previous one first waits (host synchronisation) for that hop's fold. */
 SGLB200_API int sglb200_graph_chunks(sglb200_graph_t g, int mode, int n_chunks, int64_t *tile_bounds, int64_t *row_bounds);
 SGLB200_API int sglb200_spmm_tiles(sglb200_graph_t g, const float *X, int64_t ldx, float *Y, int64_t ldy, int d, int mode,
                        int64_t tile_begin, int64_t tile_end, void *stream);
@@ -122,6 +127,20 @@ SGLB200_API int sglb200_spmm_tiles(sglb200_graph_t g, const float *X, int64_t ld
  * hops[0..K] are K+1 device pointers to [n, d] slabs with row stride ld; hops[0] holds X on entry, hops[k] receives
  * A^^k X.  Slabs may be column blocks of one [n, (K+1)*d] concat buffer (ld = (K+1)*d).  Requires n_rows==n_cols. */
 SGLB200_API int sglb200_propagate(sglb200_graph_t g, float *const *hops, int64_t ld, int d, int K, int mode, void *stream);
+
+/* ---- a1 + a4 + a8-a10/a13 fused: K hops with the degree normalisation and the cross-hop aggregation folded into the row
+ * flush of the hop kernel (models/base_model.py:23-36 = propagate, then a second pass over K+1 matrices).
+ * X: [n, d] device, row stride ldx.  hops_out: NULL, or K+1 device pointers ([n, d], row stride ld_hops) of which NULL
+ * entries are hops the caller does not want stored (hops_out[0] may equal X).  agg_op: -1 none, or an sglb200_agg value:
+ * SUM / MEAN / MAX / MIN / WEIGHTED over the hops [agg_start, agg_end) in the reference's left-to-right order (bit-exact;
+ * agg_weights: K+1 floats on the HOST indexed by hop), CONCAT (hop k goes straight into column block k-agg_start of
+ * agg_out [n, (agg_end-agg_start)*d]), OSD (all K+1 hops), LAST (hop K).  agg_out: [n, d] with row stride ld_out.
+ * fuse_norm != 0 and mode FAST and a handle whose values came from sglb200_normalize_values: the hop streams the raw
+ * weights (nothing when all are 1) and applies deg^(r-1) / deg^(-r) / the PPR teleport term in the row flush; results
+ * then differ from the materialised-values path by float32 rounding only (<= 1e-6 relative).  d <= 512. */
+SGLB200_API int sglb200_propagate_fused(sglb200_graph_t g, const float *X, int64_t ldx, float *const *hops_out, int64_t ld_hops,
+                            int d, int K, int mode, int agg_op, int agg_start, int agg_end, const float *agg_weights,
+                            float *agg_out, int64_t ld_out, int fuse_norm, void *stream);
 
 /* same with host buffers: uploads X (host [n,d] contiguous), runs K hops on the device, downloads hop k into
  * hops_out[k-1] (k = 1..K; NULL entries are skipped, e.g. keep only the last hop).  Synchronous. */

@@ -15,7 +15,7 @@ LIB_PATH = os.path.join(_PKG, "libsglb200.so")
 OK, ERR_INVALID, ERR_CUDA, ERR_NO_DEVICE, ERR_ALLOC = 0, 1, 2, 3, 4
 HOST, DEVICE = 0, 1
 MODE_FAST, MODE_EXACT = 0, 1
-AGG_SUM, AGG_MEAN, AGG_MAX, AGG_MIN, AGG_WEIGHTED, AGG_CONCAT, AGG_OSD = range(7)
+AGG_SUM, AGG_MEAN, AGG_MAX, AGG_MIN, AGG_WEIGHTED, AGG_CONCAT, AGG_OSD, AGG_LAST = range(8)
 LW_KINDS = {"simple": 0, "simple_allow_neg": 1, "gate": 2, "ori_ref": 3, "jk": 4}
 
 # every symbol include/sglb200.h declares (tests/test_abi.py checks the header against this table and the .so)
@@ -35,6 +35,8 @@ SIGNATURES = {
     "sglb200_spmm_tiles": (c_int, [c_void_p, c_void_p, c_int64, c_void_p, c_int64, c_int, c_int, c_int64, c_int64,
                                    c_void_p]),
     "sglb200_propagate": (c_int, [c_void_p, POINTER(c_void_p), c_int64, c_int, c_int, c_int, c_void_p]),
+    "sglb200_propagate_fused": (c_int, [c_void_p, c_void_p, c_int64, POINTER(c_void_p), c_int64, c_int, c_int, c_int, c_int,
+                                        c_int, c_int, POINTER(c_float), c_void_p, c_int64, c_int, c_void_p]),
     "sglb200_propagate_host": (c_int, [c_void_p, c_void_p, POINTER(c_void_p), c_int, c_int, c_int]),
     "sglb200_aggregate": (c_int, [c_int, POINTER(c_void_p), c_int, c_int64, c_int, c_int64, POINTER(c_float), c_void_p,
                                   c_int64, c_void_p]),

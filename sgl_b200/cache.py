@@ -84,8 +84,11 @@ class HopCache:
             np.save(os.path.join(tmp, f"hop_{k}.npy"), h.detach().cpu().numpy().astype(np.float32, copy=False))
         with open(os.path.join(tmp, "meta.json"), "w") as f:
             json.dump({"v": FORMAT_VERSION, "n_hops": len(hops), "shape": list(hops[0].shape)}, f)
+        import shutil
         if os.path.exists(path):        # another process won the race: keep theirs
-            import shutil
             shutil.rmtree(tmp, ignore_errors=True)
         else:
-            os.replace(tmp, path)
+            try:
+                os.replace(tmp, path)
+            except OSError:             # lost the race between the check and the rename
+                shutil.rmtree(tmp, ignore_errors=True)

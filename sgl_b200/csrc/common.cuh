@@ -47,6 +47,11 @@ struct Schedule {
     int32_t *run_row = nullptr;     // n_runs
     int64_t *run_base = nullptr;    // n_runs : first slot (carriers in tile order)
     int32_t *run_len = nullptr;     // n_runs : number of carrier tiles
+    // in-kernel fold bookkeeping (host): the arrival counters are only consistent if the tile ranges of one hop are issued
+    // completely, in order, on one stream; `next_tile` is where the current hop is expected to continue (0 = no hop open)
+    int64_t next_tile = 0;
+    cudaStream_t last_stream = nullptr;   // a hop issued on another stream first waits for this one (host sync, rare)
+    bool stream_known = false;
     std::vector<int64_t> run_last_tile;  // host copy, sorted: tile that finishes the cut row of run r (runs are
                                          // sorted by row, so a tile range maps to a contiguous run range)
 };
@@ -59,10 +64,24 @@ struct sglb200_graph {
     int64_t n_rows = 0, n_cols = 0, nnz = 0;
     int64_t *indptr = nullptr;  // n_rows+1, device
     int32_t *indices = nullptr; // nnz, device
-    float *vals = nullptr;      // nnz, device
+    float *vals = nullptr;      // nnz (+ kStreamPad), device
+    int32_t *idx_tag = nullptr; // nnz (+ kStreamPad): column id | bit 31 "last non-zero of its row" -- the stream the TMA hop
+                                // kernel walks (spmm_tma.cu); valid when empty_rows == 0
+    int64_t empty_rows = -1;    // rows without any non-zero (-1: not counted yet)
     int tile_items = 0;
     int split_threshold = 0;
     sglb200::Schedule fast, exact;
+    // fused degree normalisation (FAST mode of the fused driver): A^ = diag(row_scale) W diag(dr) (+ self_coef-weighted
+    // teleport term), W = raw weights of (A+I)^T -- filled by sglb200_normalize_values next to the exact float32 `vals`
+    bool has_scaling = false;
+    bool unit_weights = false;     // every raw weight is 1: the hop streams 4 bytes per edge (column ids only)
+    float *raw_w = nullptr;        // nnz (+ kStreamPad) raw weights, NULL when unit_weights
+    float *row_scale = nullptr;    // n_rows: fl32((1-alpha) * deg^(r-1))
+    float *col_scale = nullptr;    // n_cols: fl32(deg^-r)
+    float *self_coef = nullptr;    // n_rows: fl32(alpha / deg^-r) (PPR only, else NULL)
+    float *ping[2] = {nullptr, nullptr};  // internal hop slabs of the fused driver (n_rows * d each)
+    size_t ping_floats = 0;
+    float *aux = nullptr;          // 2 * n_rows floats (over-smoothing distance: |x| and the softmax denominator)
     float *carry_ws = nullptr;  // n_slots * ws_ld floats, grown on demand
     size_t carry_ws_floats = 0;
     float *stage[3] = {nullptr, nullptr, nullptr};  // propagate_host slabs
@@ -74,8 +93,15 @@ struct sglb200_graph {
 };
 
 namespace sglb200 {
+constexpr int64_t kStreamPad = 128;  // zeroed elements behind indices / values: bulk copies of the last chunk stay in bounds
+int build_stream_tags(sglb200_graph *g, cudaStream_t stream);
 int build_schedule(sglb200_graph *g, Schedule *s, int64_t split_threshold, cudaStream_t stream);
 void free_schedule(Schedule *s);
 int ensure_carry_ws(sglb200_graph *g, size_t floats);
+struct Epilogue;
+// one hop with every option of the fused driver: epi (NULL = plain store), raw_weights != 0 streams the raw weights
+// (or nothing when they are all 1) instead of the normalised values
+int spmm_launch_ex(sglb200_graph *g, const float *X, int64_t ldx, float *Y, int64_t ldy, int d, int mode, int accumulate,
+                   int64_t tile_begin, int64_t tile_end, const Epilogue *epi, int raw_weights, cudaStream_t stream);
 int check_device();
 }  // namespace sglb200

@@ -195,7 +195,7 @@ int build_schedule(sglb200_graph *g, Schedule *s, int64_t split_threshold, cudaS
                 }
                 t_head[(size_t)(head + len)] = (int32_t)i;   // the tile after the last carrier finishes the row
                 s->run_last_tile[i] = head + len;
-                next_slot += len;
+                next_slot += len + 1;                        // slot `len` parks the finisher's piece (fused row flush)
             }
             s->n_slots = next_slot;
             SGL_CUDA_CHECK(cudaMalloc(&s->tail_run, sizeof(int32_t) * n_tiles));
@@ -235,6 +235,44 @@ int ensure_carry_ws(sglb200_graph *g, size_t floats)
     return SGLB200_OK;
 }
 
+// idx_tag[j] = indices[j], bit 31 set on the last non-zero of every row; counts the rows without non-zeros
+__global__ void tag_row_ends_kernel(const int64_t *__restrict__ indptr, int64_t n_rows, int32_t *__restrict__ idx_tag,
+                                    unsigned long long *__restrict__ n_empty)
+{
+    const int64_t r = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (r >= n_rows) return;
+    const int64_t b = indptr[r], e = indptr[r + 1];
+    if (e > b) idx_tag[e - 1] |= (int32_t)0x80000000;
+    else atomicAdd(n_empty, 1ULL);
+}
+
+int build_stream_tags(sglb200_graph *g, cudaStream_t stream)
+{
+    if (g->idx_tag || g->nnz == 0 || g->n_rows == 0) return SGLB200_OK;
+    unsigned long long *cnt = nullptr;
+    SGL_CUDA_CHECK(cudaMalloc(&cnt, sizeof(unsigned long long)));
+    cudaError_t e = cudaMalloc(&g->idx_tag, sizeof(int32_t) * (g->nnz + kStreamPad));
+    if (e == cudaSuccess) e = cudaMemsetAsync(cnt, 0, sizeof(unsigned long long), stream);
+    if (e == cudaSuccess) e = cudaMemsetAsync(g->idx_tag + g->nnz, 0, sizeof(int32_t) * kStreamPad, stream);
+    if (e == cudaSuccess) e = cudaMemcpyAsync(g->idx_tag, g->indices, sizeof(int32_t) * g->nnz, cudaMemcpyDeviceToDevice, stream);
+    if (e == cudaSuccess) {
+        tag_row_ends_kernel<<<(unsigned)((g->n_rows + 255) / 256), 256, 0, stream>>>(g->indptr, g->n_rows, g->idx_tag, cnt);
+        e = cudaGetLastError();
+    }
+    unsigned long long h = 0;
+    if (e == cudaSuccess) e = cudaMemcpyAsync(&h, cnt, sizeof(h), cudaMemcpyDeviceToHost, stream);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(stream);
+    cudaFree(cnt);
+    if (e != cudaSuccess) {
+        cudaFree(g->idx_tag);
+        g->idx_tag = nullptr;
+        SGL_CUDA_CHECK(e);
+    }
+    g->empty_rows = (int64_t)h;
+    g->bytes_resident += sizeof(int32_t) * (size_t)(g->nnz + kStreamPad);
+    return SGLB200_OK;
+}
+
 __global__ void widen_indptr_kernel(const int32_t *__restrict__ in, int64_t *__restrict__ out, int64_t n)
 {
     const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
@@ -261,6 +299,28 @@ __global__ void normalize_values_kernel(const int64_t *__restrict__ indptr, cons
         }
         vals[j] = (float)v;
     }
+}
+
+// float32 copies for the fused normalisation: raw weights, (1-alpha)*dL, dR, alpha/dR; flags[0] counts non-unit weights
+__global__ void scaling_vectors_kernel(const double *__restrict__ d_left, const double *__restrict__ d_right, double one_minus_alpha,
+                                       double alpha, int apply_ppr, int64_t n, float *__restrict__ row_scale,
+                                       float *__restrict__ col_scale, float *__restrict__ self_coef)
+{
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const double dl = d_left[i], dr = d_right[i];
+    row_scale[i] = (float)(apply_ppr ? one_minus_alpha * dl : dl);
+    col_scale[i] = (float)dr;
+    if (self_coef) self_coef[i] = dr != 0.0 ? (float)(alpha / dr) : 0.0f;
+}
+__global__ void raw_weights_kernel(const double *__restrict__ raw_w, int64_t nnz, float *__restrict__ out,
+                                   unsigned long long *__restrict__ non_unit)
+{
+    const int64_t j = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (j >= nnz) return;
+    const double w = raw_w[j];
+    out[j] = (float)w;
+    if (w != 1.0) atomicAdd(non_unit, 1ULL);
 }
 
 }  // namespace sglb200
@@ -361,7 +421,8 @@ int sglb200_graph_create(sglb200_graph_t *out, int64_t n_rows, int64_t n_cols, i
     const cudaMemcpyKind kind = loc == SGLB200_HOST ? cudaMemcpyHostToDevice : cudaMemcpyDeviceToDevice;
     G_CHECK(cudaMalloc(&g->indptr, sizeof(int64_t) * (n_rows + 1)));
     G_CHECK(cudaMalloc(&g->indices, sizeof(int32_t) * (nnz > 0 ? nnz : 1)));
-    G_CHECK(cudaMalloc(&g->vals, sizeof(float) * (nnz > 0 ? nnz : 1)));
+    G_CHECK(cudaMalloc(&g->vals, sizeof(float) * (nnz + kStreamPad)));
+    G_CHECK(cudaMemsetAsync(g->vals + nnz, 0, sizeof(float) * kStreamPad, stream));
     g->bytes_resident = sizeof(int64_t) * (n_rows + 1) + 8 * (size_t)nnz;
     if (indptr_is64) {
         G_CHECK(cudaMemcpyAsync(g->indptr, indptr, sizeof(int64_t) * (n_rows + 1), kind, stream));
@@ -415,6 +476,14 @@ int sglb200_graph_destroy(sglb200_graph_t g)
     cudaFree(g->indptr);
     cudaFree(g->indices);
     cudaFree(g->vals);
+    cudaFree(g->idx_tag);
+    cudaFree(g->raw_w);
+    cudaFree(g->row_scale);
+    cudaFree(g->col_scale);
+    cudaFree(g->self_coef);
+    cudaFree(g->ping[0]);
+    cudaFree(g->ping[1]);
+    cudaFree(g->aux);
     cudaFree(g->carry_ws);
     for (int k = 0; k < 3; ++k) {
         cudaFree(g->stage[k]);
@@ -508,6 +577,39 @@ int sglb200_normalize_values(sglb200_graph_t g, const double *raw_w, const doubl
             g->indptr, g->indices, w, dl, dr, 1.0 - alpha, alpha, apply_ppr, g->n_rows, g->vals);
     }
     cudaError_t e = cudaGetLastError();
+    // float32 scaling vectors + raw weights for the fused normalisation of the fused driver (FAST mode)
+    if (e == cudaSuccess && g->n_rows > 0 && g->nnz > 0) {
+        const size_t n = (size_t)g->n_rows, m = (size_t)g->nnz;
+        unsigned long long *cnt = nullptr;
+        cudaFree(g->raw_w); cudaFree(g->row_scale); cudaFree(g->col_scale); cudaFree(g->self_coef);
+        g->raw_w = g->row_scale = g->col_scale = g->self_coef = nullptr;
+        g->has_scaling = false;
+        e = cudaMalloc(&cnt, sizeof(unsigned long long));
+        if (e == cudaSuccess) e = cudaMemsetAsync(cnt, 0, sizeof(unsigned long long), stream);
+        if (e == cudaSuccess) e = cudaMalloc(&g->raw_w, sizeof(float) * (m + kStreamPad));
+        if (e == cudaSuccess) e = cudaMemsetAsync(g->raw_w + m, 0, sizeof(float) * kStreamPad, stream);
+        if (e == cudaSuccess) e = cudaMalloc(&g->row_scale, sizeof(float) * n);
+        if (e == cudaSuccess) e = cudaMalloc(&g->col_scale, sizeof(float) * n);
+        if (e == cudaSuccess && apply_ppr) e = cudaMalloc(&g->self_coef, sizeof(float) * n);
+        if (e == cudaSuccess) {
+            scaling_vectors_kernel<<<(unsigned)((n + 255) / 256), 256, 0, stream>>>(dl, dr, 1.0 - alpha, alpha, apply_ppr, (int64_t)n,
+                                                                                   g->row_scale, g->col_scale, g->self_coef);
+            raw_weights_kernel<<<(unsigned)((m + 255) / 256), 256, 0, stream>>>(w, (int64_t)m, g->raw_w, cnt);
+            e = cudaGetLastError();
+        }
+        unsigned long long non_unit = 1;
+        if (e == cudaSuccess) e = cudaMemcpyAsync(&non_unit, cnt, sizeof(non_unit), cudaMemcpyDeviceToHost, stream);
+        if (e == cudaSuccess) e = cudaStreamSynchronize(stream);
+        cudaFree(cnt);
+        if (e == cudaSuccess) {
+            g->has_scaling = true;
+            g->unit_weights = non_unit == 0;
+            if (g->unit_weights) {
+                cudaFree(g->raw_w);
+                g->raw_w = nullptr;
+            }
+        }
+    }
     if (tmp) {
         if (e == cudaSuccess) e = cudaStreamSynchronize(stream);
         cudaFree(tmp);

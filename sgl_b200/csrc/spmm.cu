@@ -25,164 +25,17 @@
 
 #include <algorithm>
 
-#include "common.cuh"
+#include "spmm_common.cuh"
 
 namespace sglb200 {
 
-constexpr int kWarpsPerBlock = 8;
-constexpr unsigned kFull = 0xffffffffu;
-
-struct SpmmParams {
-    const int64_t *indptr;
-    const int32_t *indices;
-    const float *vals;
-    const int32_t *tile_row;
-    const int64_t *tile_nnz;
-    const int32_t *carry_slot;
-    int64_t tile_begin;  // first tile of this launch
-    int64_t n_tiles;     // one past the last tile of this launch
-    int64_t n_rows;
-    const float *X;
-    int64_t ldx;
-    float *Y;
-    int64_t ldy;
-    int d;
-    float *carry_ws;
-    int64_t ws_ld;
-    int stream_y;  // 1: output rows are stored with the streaming (evict-first) policy
-    // L2 residency control for gathered rows: columns below hub_cols are loaded with an evict_last policy, the
-    // rest with cold_policy (0 = no hint, 1 = evict_first); hub_cols == 0 disables the hints
-    uint32_t hub_cols;
-    int cold_policy;
-    // in-kernel fold of cut rows (fold != 0): every tile that holds a piece of a cut row stores its partial in the
-    // workspace and arrives on the row's counter; the LAST arriver adds the partials in tile order and writes Y
-    int fold;
-    const int32_t *tail_run;
-    const int32_t *head_run;
-    const int32_t *run_row;
-    const int64_t *run_base;
-    const int32_t *run_len;
-    unsigned int *run_count;
-};
-
-// gathered feature rows: read-only path, L1-allocating (hub rows of skewed graphs are re-read by neighbouring warps)
-template <int VEC> __device__ __forceinline__ void load_row_slice(float (&r)[VEC], const float *p)
+// FLAG: the column stream is the tagged one (idx_tag: bit 31 = last non-zero of its row; graphs without empty rows), so a
+// row ends where the stream says so: no row-pointer window, no countdown -- fewer live registers, more resident warps.
+template <int VEC, int VPL, int U, bool ACCUM, int MINB, int PIPE, bool HINT = false, bool EPI = false, bool FLAG = false>
+__global__ void __launch_bounds__(kWarpsPerBlock * 32, MINB) spmm_flat_kernel(const SpmmParams p, const int32_t *__restrict__ idx_tag)
 {
-    if constexpr (VEC == 4) {
-        const float4 v = __ldg(reinterpret_cast<const float4 *>(p));
-        r[0] = v.x; r[1] = v.y; r[2] = v.z; r[3] = v.w;
-    } else if constexpr (VEC == 2) {
-        const float2 v = __ldg(reinterpret_cast<const float2 *>(p));
-        r[0] = v.x; r[1] = v.y;
-    } else {
-        r[0] = __ldg(p);
-    }
-}
-template <int VEC> __device__ __forceinline__ void load_plain(float (&r)[VEC], const float *p)
-{
-    if constexpr (VEC == 4) {
-        const float4 v = *reinterpret_cast<const float4 *>(p);
-        r[0] = v.x; r[1] = v.y; r[2] = v.z; r[3] = v.w;
-    } else if constexpr (VEC == 2) {
-        const float2 v = *reinterpret_cast<const float2 *>(p);
-        r[0] = v.x; r[1] = v.y;
-    } else {
-        r[0] = *p;
-    }
-}
-template <int VEC> __device__ __forceinline__ void store_slice(float *p, const float (&r)[VEC])
-{
-    if constexpr (VEC == 4) *reinterpret_cast<float4 *>(p) = make_float4(r[0], r[1], r[2], r[3]);
-    else if constexpr (VEC == 2) *reinterpret_cast<float2 *>(p) = make_float2(r[0], r[1]);
-    else *p = r[0];
-}
-// the CSR stream is touched once per hop: keep it out of L1
-__device__ __forceinline__ int32_t load_stream_i32(const int32_t *p)
-{
-    int32_t v;
-    asm volatile("ld.global.cs.s32 %0, [%1];" : "=r"(v) : "l"(p));
-    return v;
-}
-__device__ __forceinline__ float load_stream_f32(const float *p)
-{
-    float v;
-    asm volatile("ld.global.cs.f32 %0, [%1];" : "=f"(v) : "l"(p));
-    return v;
-}
-
-// A lane's slice of a feature row: VEC floats kept as packed fp32 pairs so that the accumulation is issued as
-// FFMA2 (fma.rn.f32x2, sm_100): two IEEE fused multiply-adds per instruction, bit-identical to two fmaf.
-template <int VEC> struct Slice;
-template <> struct Slice<4> {
-    ulonglong2 v;
-    __device__ __forceinline__ void zero() { v.x = 0ULL; v.y = 0ULL; }
-    __device__ __forceinline__ void load_nc(const char *p) { v = __ldg(reinterpret_cast<const ulonglong2 *>(p)); }
-    __device__ __forceinline__ void load(const char *p) { v = *reinterpret_cast<const ulonglong2 *>(p); }
-    __device__ __forceinline__ void load_l2(const char *p) { v = __ldcg(reinterpret_cast<const ulonglong2 *>(p)); }
-    __device__ __forceinline__ void load_hint(const char *p, uint64_t pol)
-    {
-        asm volatile("ld.global.nc.L1::no_allocate.L2::cache_hint.v2.u64 {%0, %1}, [%2], %3;"
-                     : "=l"(v.x), "=l"(v.y) : "l"(p), "l"(pol));
-    }
-    __device__ __forceinline__ void add(const Slice &x)
-    {
-        asm("add.rn.f32x2 %0, %0, %2; add.rn.f32x2 %1, %1, %3;" : "+l"(v.x), "+l"(v.y) : "l"(x.v.x), "l"(x.v.y));
-    }
-    __device__ __forceinline__ void store(char *p) const { *reinterpret_cast<ulonglong2 *>(p) = v; }
-    // output rows are written once and not re-read by this hop: streaming store, so they do not evict X from L2
-    __device__ __forceinline__ void store_streaming(char *p) const
-    {
-        asm volatile("st.global.cs.v2.u64 [%0], {%1, %2};" ::"l"(p), "l"(v.x), "l"(v.y) : "memory");
-    }
-    __device__ __forceinline__ void fma(float w, const Slice &x)
-    {
-        asm("{ .reg .b64 ww; mov.b64 ww, {%2, %2}; fma.rn.f32x2 %0, ww, %3, %0; fma.rn.f32x2 %1, ww, %4, %1; }"
-            : "+l"(v.x), "+l"(v.y) : "f"(w), "l"(x.v.x), "l"(x.v.y));
-    }
-};
-template <> struct Slice<2> {
-    unsigned long long v;
-    __device__ __forceinline__ void zero() { v = 0ULL; }
-    __device__ __forceinline__ void load_nc(const char *p) { v = __ldg(reinterpret_cast<const unsigned long long *>(p)); }
-    __device__ __forceinline__ void load(const char *p) { v = *reinterpret_cast<const unsigned long long *>(p); }
-    __device__ __forceinline__ void load_l2(const char *p) { v = __ldcg(reinterpret_cast<const unsigned long long *>(p)); }
-    __device__ __forceinline__ void load_hint(const char *p, uint64_t pol)
-    {
-        asm volatile("ld.global.nc.L1::no_allocate.L2::cache_hint.u64 %0, [%1], %2;" : "=l"(v) : "l"(p), "l"(pol));
-    }
-    __device__ __forceinline__ void add(const Slice &x) { asm("add.rn.f32x2 %0, %0, %1;" : "+l"(v) : "l"(x.v)); }
-    __device__ __forceinline__ void store(char *p) const { *reinterpret_cast<unsigned long long *>(p) = v; }
-    __device__ __forceinline__ void store_streaming(char *p) const
-    {
-        asm volatile("st.global.cs.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
-    }
-    __device__ __forceinline__ void fma(float w, const Slice &x)
-    {
-        asm("{ .reg .b64 ww; mov.b64 ww, {%1, %1}; fma.rn.f32x2 %0, ww, %2, %0; }" : "+l"(v) : "f"(w), "l"(x.v));
-    }
-};
-template <> struct Slice<1> {
-    float v;
-    __device__ __forceinline__ void zero() { v = 0.0f; }
-    __device__ __forceinline__ void load_nc(const char *p) { v = __ldg(reinterpret_cast<const float *>(p)); }
-    __device__ __forceinline__ void load(const char *p) { v = *reinterpret_cast<const float *>(p); }
-    __device__ __forceinline__ void load_l2(const char *p) { v = __ldcg(reinterpret_cast<const float *>(p)); }
-    __device__ __forceinline__ void load_hint(const char *p, uint64_t pol)
-    {
-        asm volatile("ld.global.nc.L1::no_allocate.L2::cache_hint.f32 %0, [%1], %2;" : "=f"(v) : "l"(p), "l"(pol));
-    }
-    __device__ __forceinline__ void add(const Slice &x) { v = __fadd_rn(v, x.v); }
-    __device__ __forceinline__ void store(char *p) const { *reinterpret_cast<float *>(p) = v; }
-    __device__ __forceinline__ void store_streaming(char *p) const
-    {
-        asm volatile("st.global.cs.f32 [%0], %1;" ::"l"(p), "f"(v) : "memory");
-    }
-    __device__ __forceinline__ void fma(float w, const Slice &x) { v = fmaf(w, x.v, v); }
-};
-
-template <int VEC, int VPL, int U, bool ACCUM, int MINB, int PIPE, bool HINT = false>
-__global__ void __launch_bounds__(kWarpsPerBlock * 32, MINB) spmm_flat_kernel(const SpmmParams p)
-{
+    static_assert(!(FLAG && ACCUM), "the flagged walk starts every chain from zero");
+    static_assert(!(EPI && ACCUM), "the fused row flush starts every chain from zero");
     static_assert(32 % U == 0, "U must divide the batch of 32 non-zeros");
     static_assert(PIPE == 1 || PIPE == 2, "one or two groups of gathers in flight per warp");
     // (column id, value bits) of two batches of 32 non-zeros per warp: one LDS.128 broadcast hands every lane two
@@ -204,16 +57,27 @@ __global__ void __launch_bounds__(kWarpsPerBlock * 32, MINB) spmm_flat_kernel(co
     // Row addresses are ONE 32x32->64 multiply-add each: base pointer (kept in registers) + id * stride-in-bytes.
     const int col_block = blockIdx.y * (32 * VEC * VPL);
     bool act[VPL];
+    int cofs_v[VPL];
     const char *xbase[VPL];
     char *ybase[VPL];
 #pragma unroll
     for (int v = 0; v < VPL; ++v) {
         const int cofs = col_block + (v * 32 + lane) * VEC;
+        cofs_v[v] = cofs;
         act[v] = cofs < p.d;
         xbase[v] = reinterpret_cast<const char *>(p.X) + (size_t)(act[v] ? cofs : col_block) * sizeof(float);
         ybase[v] = reinterpret_cast<char *>(p.Y) + (size_t)cofs * sizeof(float);
         asm volatile("" : "+l"(xbase[v]));  // materialise: keeps the compiler from re-adding the parameter every load
         asm volatile("" : "+l"(ybase[v]));
+    }
+    // fused row flush: a tile whose first row continues a cut row parks that piece in the workspace (slot after the
+    // row's carriers) instead of flushing it; the tile that completes the row's arrivals performs the one real flush
+    int cont_slot = -1;
+    if constexpr (EPI) {
+        if (p.fold) {
+            const int hr = p.head_run[t];
+            if (hr >= 0) cont_slot = (int)(p.run_base[hr] + p.run_len[hr]);
+        }
     }
     const uint32_t ldx_bytes = (uint32_t)p.ldx * (uint32_t)sizeof(float);  // strides < 2^30 elements (host check)
     const uint32_t ldy_bytes = (uint32_t)p.ldy * (uint32_t)sizeof(float);
@@ -237,9 +101,9 @@ __global__ void __launch_bounds__(kWarpsPerBlock * 32, MINB) spmm_flat_kernel(co
         return rel > (int64_t)INT_MAX ? INT_MAX : (int)rel;
     };
     int row_base = row;
-    int my_end = load_row_ends(row_base);
+    int my_end = FLAG ? 0 : load_row_ends(row_base);
     // next_end: tile-relative position at which the current row ends; INT_MAX once the tile owns no further row end
-    int next_end = __shfl_sync(kFull, my_end, 0);
+    int next_end = FLAG ? 0 : __shfl_sync(kFull, my_end, 0);
     if (row >= row_end) next_end = INT_MAX;
 
     if (ACCUM) {
@@ -251,23 +115,41 @@ __global__ void __launch_bounds__(kWarpsPerBlock * 32, MINB) spmm_flat_kernel(co
     }
 
     auto flush_row = [&]() {
+        if constexpr (EPI) {
+            if (cont_slot >= 0) {
+                char *wrow = reinterpret_cast<char *>(p.carry_ws + (int64_t)cont_slot * p.ws_ld);
 #pragma unroll
-        for (int v = 0; v < VPL; ++v)
-            if (act[v]) {
-                if (p.stream_y) acc[v].store_streaming(ybase[v] + (uint64_t)(uint32_t)row * ldy_bytes);
-                else acc[v].store(ybase[v] + (uint64_t)(uint32_t)row * ldy_bytes);
+                for (int v = 0; v < VPL; ++v)
+                    if (act[v]) acc[v].store(wrow + (size_t)cofs_v[v] * sizeof(float));
+                cont_slot = -1;
+            } else {
+                emit_row<VEC, VPL, 32>(p, (uint32_t)row, acc, act, cofs_v, kFull);
             }
-        ++row;
-        if (row - row_base == 32) {
-            row_base = row;
-            my_end = load_row_ends(row_base);
+        } else {
+#pragma unroll
+            for (int v = 0; v < VPL; ++v)
+                if (act[v]) {
+                    if (p.stream_y) acc[v].store_streaming(ybase[v] + (uint64_t)(uint32_t)row * ldy_bytes);
+                    else acc[v].store(ybase[v] + (uint64_t)(uint32_t)row * ldy_bytes);
+                }
         }
-        const int e = __shfl_sync(kFull, my_end, row - row_base);
-        next_end = row < row_end ? e : INT_MAX;
+        ++row;
+        if constexpr (!FLAG) {
+            if (row - row_base == 32) {
+                row_base = row;
+                my_end = load_row_ends(row_base);
+            }
+            const int e = __shfl_sync(kFull, my_end, row - row_base);
+            next_end = row < row_end ? e : INT_MAX;
+        }
         init_acc(row);  // every later row of the tile starts inside the tile
     };
+    if constexpr (FLAG) {
+        // the one row a flag cannot retire: a cut row whose non-zeros all lie in earlier tiles
+        if (row < row_end && p.indptr[row + 1] == j0) flush_row();
+    }
 
-    const int32_t *cols = p.indices + j0;
+    const int32_t *cols = (FLAG ? idx_tag : p.indices) + j0;
     const float *vals = p.vals + j0;
     uint64_t pol_hub = 0, pol_cold = 0;
     if constexpr (HINT) {
@@ -280,9 +162,10 @@ __global__ void __launch_bounds__(kWarpsPerBlock * 32, MINB) spmm_flat_kernel(co
     // (col, val) of the next 32 non-zeros are fetched into registers one batch ahead of their publication
     int32_t col_next = 0;
     float val_next = 0.0f;
+    const bool unit_w = p.vals == nullptr;   // fused normalisation on an unweighted graph: 4 bytes per edge
     if (lane < n_nnz) {
         col_next = load_stream_i32(cols + lane);
-        val_next = load_stream_f32(vals + lane);
+        val_next = unit_w ? 1.0f : load_stream_f32(vals + lane);
     }
     // lanes past the end of the tile publish (column 0, weight 0): a valid row to gather, never accumulated
     auto publish_batch = [&](int b) {
@@ -294,7 +177,7 @@ __global__ void __launch_bounds__(kWarpsPerBlock * 32, MINB) spmm_flat_kernel(co
         const int nb = (b + 1) * 32 + lane;
         if (nb < n_nnz) {
             col_next = load_stream_i32(cols + nb);
-            val_next = load_stream_f32(vals + nb);
+            val_next = unit_w ? 1.0f : load_stream_f32(vals + nb);
         }
     };
 
@@ -306,8 +189,7 @@ __global__ void __launch_bounds__(kWarpsPerBlock * 32, MINB) spmm_flat_kernel(co
         const int2 *pp = pairs + (pos & 63);
 #pragma unroll
         for (int u = 0; u < U; ++u) {
-            const uint32_t c = (uint32_t)pp[u].x;
-#pragma unroll
+            const uint32_t c = (uint32_t)pp[u].x & (FLAG ? 0x3fffffffu : 0xffffffffu);
             if constexpr (HINT) {
                 const uint64_t pol = c < hub_cols ? pol_hub : pol_cold;
 #pragma unroll
@@ -321,6 +203,19 @@ __global__ void __launch_bounds__(kWarpsPerBlock * 32, MINB) spmm_flat_kernel(co
     auto consume = [&](Slice<VEC> (&buf)[U][VPL], int g) {
         const int pos = g * U;
         const int2 *pp = pairs + (pos & 63);
+        if constexpr (FLAG) {
+            const int valid = n_nnz - pos;
+#pragma unroll
+            for (int u = 0; u < U; ++u) {
+                const int2 cw = pp[u];
+                if (u < valid) {   // warp-uniform
+#pragma unroll
+                    for (int v = 0; v < VPL; ++v) acc[v].fma(__int_as_float(cw.y), buf[u][v]);
+                    if (cw.x < 0 && row < row_end) flush_row();
+                }
+            }
+            return;
+        }
         int left = next_end - pos;  // non-zeros of the current row still ahead, counted from the group start
         if (left >= U && n_nnz - pos >= U) {
             // the whole group belongs to the current row: no row-end checks, no predicates
@@ -402,20 +297,38 @@ __global__ void __launch_bounds__(kWarpsPerBlock * 32, MINB) spmm_flat_kernel(co
                 const char *ws0 = reinterpret_cast<const char *>(p.carry_ws + p.run_base[run] * p.ws_ld);
                 const size_t ws_ld_bytes = (size_t)p.ws_ld * sizeof(float);
                 const uint32_t out_row = (uint32_t)p.run_row[run];
+                if constexpr (EPI) {
+                    // c0 + c1 + ... + finisher piece (slot n_carriers), then the one real flush of the row
+                    Slice<VEC> sum[VPL];
 #pragma unroll
-                for (int v = 0; v < VPL; ++v) {
-                    if (!act[v]) continue;
-                    const size_t cb = (size_t)(col_block + (v * 32 + lane) * VEC) * sizeof(float);
-                    Slice<VEC> sum, part;
-                    sum.load_l2(ws0 + cb);
-                    for (int u = 1; u < n_carriers; ++u) {
-                        part.load_l2(ws0 + (size_t)u * ws_ld_bytes + cb);
-                        sum.add(part);
+                    for (int v = 0; v < VPL; ++v) {
+                        sum[v].zero();
+                        if (!act[v]) continue;
+                        const size_t cb = (size_t)cofs_v[v] * sizeof(float);
+                        Slice<VEC> part;
+                        sum[v].load_l2(ws0 + cb);
+                        for (int u = 1; u <= n_carriers; ++u) {
+                            part.load_l2(ws0 + (size_t)u * ws_ld_bytes + cb);
+                            sum[v].add(part);
+                        }
                     }
-                    char *yp = ybase[v] + (uint64_t)out_row * ldy_bytes;
-                    part.load_l2(yp);          // the finishing tile's partial
-                    part.add(sum);             // Y = finisher + (c0 + c1 + ...): the order of the separate fold kernel
-                    part.store(yp);
+                    emit_row<VEC, VPL, 32>(p, out_row, sum, act, cofs_v, kFull);
+                } else {
+#pragma unroll
+                    for (int v = 0; v < VPL; ++v) {
+                        if (!act[v]) continue;
+                        const size_t cb = (size_t)(col_block + (v * 32 + lane) * VEC) * sizeof(float);
+                        Slice<VEC> sum, part;
+                        sum.load_l2(ws0 + cb);
+                        for (int u = 1; u < n_carriers; ++u) {
+                            part.load_l2(ws0 + (size_t)u * ws_ld_bytes + cb);
+                            sum.add(part);
+                        }
+                        char *yp = ybase[v] + (uint64_t)out_row * ldy_bytes;
+                        part.load_l2(yp);          // the finishing tile's partial
+                        part.add(sum);             // Y = finisher + (c0 + c1 + ...): the order of the separate fold kernel
+                        part.store(yp);
+                    }
                 }
                 if (lane == 0) p.run_count[run] = 0u;  // ready for the next hop
             }
@@ -651,7 +564,7 @@ static cudaError_t launch_windowed(Kern kern, const SpmmParams &p, dim3 grid, cu
     // experiment: pin the first window_mb MB of X in L2 through a per-launch access policy window
     static int window_mb = env_int("SGLB200_L2_WINDOW_MB", 0);
     if (window_mb <= 0) {
-        kern<<<grid, kWarpsPerBlock * 32, 0, stream>>>(p);
+        kern<<<grid, kWarpsPerBlock * 32, 0, stream>>>(p, nullptr);
         return cudaGetLastError();
     }
     static bool limit_set = false;
@@ -672,19 +585,33 @@ static cudaError_t launch_windowed(Kern kern, const SpmmParams &p, dim3 grid, cu
     attr[0].val.accessPolicyWindow.missProp = cudaAccessPropertyStreaming;
     cfg.attrs = attr;
     cfg.numAttrs = 1;
-    return cudaLaunchKernelEx(&cfg, kern, p);
+    return cudaLaunchKernelEx(&cfg, kern, p, (const int32_t *)nullptr);
 }
+
+static const int32_t *g_flat_tags = nullptr;   // set by spmm_launch_ex for the duration of one launch (host, single thread per handle)
 
 template <int VEC, int VPL, int U, int MINB, int PIPE = 1>
 static cudaError_t launch_flat(const SpmmParams &p, bool accum, dim3 grid, cudaStream_t stream)
 {
+    const int32_t *tags = accum ? nullptr : g_flat_tags;
+    if (!accum && p.epi.active) {
+        if (tags) spmm_flat_kernel<VEC, VPL, U, false, (MINB > 3 ? 3 : MINB), 1, false, true, true><<<grid, kWarpsPerBlock * 32, 0, stream>>>(p, tags);
+        else spmm_flat_kernel<VEC, VPL, U, false, (MINB > 3 ? 3 : MINB), 1, false, true><<<grid, kWarpsPerBlock * 32, 0, stream>>>(p, nullptr);
+        return cudaGetLastError();
+    }
+    if (!accum && tags && p.hub_cols == 0) {
+        static int minb4 = env_int("SGLB200_FLAG_MINB4", 0);
+        if (VEC == 4 && VPL == 1 && minb4) spmm_flat_kernel<VEC, VPL, U, false, (VEC == 4 && VPL == 1 ? 4 : MINB), 1, false, false, true><<<grid, kWarpsPerBlock * 32, 0, stream>>>(p, tags);
+        else spmm_flat_kernel<VEC, VPL, U, false, MINB, 1, false, false, true><<<grid, kWarpsPerBlock * 32, 0, stream>>>(p, tags);
+        return cudaGetLastError();
+    }
     if (!accum && p.hub_cols > 0) {
-        spmm_flat_kernel<VEC, VPL, U, false, MINB, PIPE, true><<<grid, kWarpsPerBlock * 32, 0, stream>>>(p);
+        spmm_flat_kernel<VEC, VPL, U, false, MINB, PIPE, true><<<grid, kWarpsPerBlock * 32, 0, stream>>>(p, nullptr);
         return cudaGetLastError();
     }
     if (!accum) return launch_windowed(spmm_flat_kernel<VEC, VPL, U, false, MINB, PIPE>, p, grid, stream);
-    if (accum) spmm_flat_kernel<VEC, VPL, U, true, (MINB > 3 ? 3 : MINB), 1><<<grid, kWarpsPerBlock * 32, 0, stream>>>(p);
-    else spmm_flat_kernel<VEC, VPL, U, false, MINB, PIPE><<<grid, kWarpsPerBlock * 32, 0, stream>>>(p);
+    if (accum) spmm_flat_kernel<VEC, VPL, U, true, (MINB > 3 ? 3 : MINB), 1><<<grid, kWarpsPerBlock * 32, 0, stream>>>(p, nullptr);
+    else spmm_flat_kernel<VEC, VPL, U, false, MINB, PIPE><<<grid, kWarpsPerBlock * 32, 0, stream>>>(p, nullptr);
     return cudaGetLastError();
 }
 
@@ -729,6 +656,9 @@ static void pick_shape(int d, int max_vec, int *vec_out, int *vpl_out, int *col_
 
 int spmm_launch_tiles(sglb200_graph *g, const float *X, int64_t ldx, float *Y, int64_t ldy, int d, int mode,
                       int accumulate, int64_t tile_begin, int64_t tile_end, cudaStream_t stream);
+cudaError_t spmm_group_launch(const SpmmParams &p, bool accum, const int32_t *idx_tag, cudaStream_t stream);  // spmm_group.cu
+bool spmm_tma_eligible(const sglb200_graph *g, const float *X, int64_t ldx, int d);      // spmm_tma.cu
+cudaError_t spmm_tma_launch(const sglb200_graph *g, const SpmmParams &p, cudaStream_t stream);
 
 int spmm_launch(sglb200_graph *g, const float *X, int64_t ldx, float *Y, int64_t ldy, int d, int mode, int accumulate,
                 cudaStream_t stream)
@@ -741,11 +671,20 @@ int spmm_launch(sglb200_graph *g, const float *X, int64_t ldx, float *Y, int64_t
 int spmm_launch_tiles(sglb200_graph *g, const float *X, int64_t ldx, float *Y, int64_t ldy, int d, int mode,
                       int accumulate, int64_t tile_begin, int64_t tile_end, cudaStream_t stream)
 {
+    return spmm_launch_ex(g, X, ldx, Y, ldy, d, mode, accumulate, tile_begin, tile_end, nullptr, 0, stream);
+}
+
+int spmm_launch_ex(sglb200_graph *g, const float *X, int64_t ldx, float *Y, int64_t ldy, int d, int mode, int accumulate,
+                   int64_t tile_begin, int64_t tile_end, const Epilogue *epi, int raw_weights, cudaStream_t stream)
+{
     SGL_REQUIRE(g != nullptr, "spmm: graph is NULL");
     SGL_REQUIRE(d >= 0, "spmm: negative feature width");
     if (g->n_rows == 0 || d == 0) return SGLB200_OK;
-    SGL_REQUIRE(X != nullptr && Y != nullptr, "spmm: X or Y is NULL");
-    SGL_REQUIRE(ldx >= d && ldy >= d, "spmm: row stride smaller than the feature width");
+    SGL_REQUIRE(X != nullptr && (Y != nullptr || epi != nullptr), "spmm: X or Y is NULL");
+    SGL_REQUIRE(ldx >= d && (Y == nullptr || ldy >= d), "spmm: row stride smaller than the feature width");
+    SGL_REQUIRE(!(epi && accumulate), "spmm: the fused row flush cannot accumulate into Y");
+    SGL_REQUIRE(!raw_weights || g->has_scaling, "spmm: the handle holds no raw weights (sglb200_normalize_values)");
+    if (Y == nullptr) ldy = d;
     SGL_REQUIRE(ldx < (1LL << 30) && ldy < (1LL << 30), "spmm: row stride must be below 2^30 elements");
     SGL_REQUIRE(mode == SGLB200_MODE_FAST || mode == SGLB200_MODE_EXACT, "spmm: unknown mode %d", mode);
     Schedule *s = &g->fast;
@@ -763,7 +702,7 @@ int spmm_launch_tiles(sglb200_graph *g, const float *X, int64_t ldx, float *Y, i
         // experiment: column tiling -- the hop runs once per block of col_tile feature columns so that the hub rows
         // of one block (col_tile * 4 bytes each) fit L2 in larger numbers
         static int col_tile = env_int("SGLB200_COL_TILE", 0);
-        if (col_tile > 0 && d > col_tile && d % col_tile == 0 && !accumulate) {
+        if (col_tile > 0 && d > col_tile && d % col_tile == 0 && !accumulate && !epi && !raw_weights) {
             for (int c0 = 0; c0 < d; c0 += col_tile) {
                 const int st = spmm_launch_tiles(g, X + c0, ldx, Y + c0, ldy, col_tile, mode, 0, tile_begin, tile_end, stream);
                 if (st != SGLB200_OK) return st;
@@ -776,20 +715,48 @@ int spmm_launch_tiles(sglb200_graph *g, const float *X, int64_t ldx, float *Y, i
     if (tile_begin >= tile_end) return SGLB200_OK;
 
     int max_vec = 4;
-    if (d % 4 || ldx % 4 || ldy % 4 || !aligned(X, 16) || !aligned(Y, 16)) max_vec = 2;
-    if (max_vec == 2 && (d % 2 || ldx % 2 || ldy % 2 || !aligned(X, 8) || !aligned(Y, 8))) max_vec = 1;
+    auto fits = [&](int64_t ld, const void *ptr, int v) { return ptr == nullptr || (ld % v == 0 && aligned(ptr, 4 * v)); };
+    auto all_fit = [&](int v) {
+        bool ok = d % v == 0 && fits(ldx, X, v) && fits(ldy, Y, v);
+        if (epi) ok = ok && fits(epi->ldz, epi->Z, v) && fits(epi->ld_agg, epi->agg, v) && fits(epi->ld_self, epi->self_x, v) &&
+                  fits(epi->ldx0, epi->x0, v);
+        return ok;
+    };
+    if (!all_fit(4)) max_vec = 2;
+    if (max_vec == 2 && !all_fit(2)) max_vec = 1;
     int vec, vpl, col_blocks;
     pick_shape(d, max_vec, &vec, &vpl, &col_blocks);
+    // narrow float4 rows: 32/G tiles per warp, one lane group each (spmm_group.cu)
+    const bool use_groups = max_vec == 4 && d <= 64 && spmm_variant() < 10 && env_int("SGLB200_GROUP", 1) != 0;
+    if (use_groups) {
+        vec = 4;
+        vpl = 1;
+        col_blocks = 1;
+    }
 
+    // TMA-staged kernel (spmm_tma.cu): float4 rows of 64..256 floats on graphs without empty rows
+    bool use_tma = false;
+    if (!accumulate && !use_groups && max_vec == 4 && d > 64 && d <= 128 && spmm_variant() < 10 && env_int("SGLB200_TMA", 0) != 0) {
+        if (g->empty_rows < 0) {
+            const int st = build_stream_tags(g, stream);
+            if (st != SGLB200_OK) return st;
+        }
+        use_tma = spmm_tma_eligible(g, X, ldx, d);
+        if (use_tma) {
+            vec = 4;
+            vpl = 1;
+            col_blocks = 1;
+        }
+    }
     const int64_t ws_ld = (d + 3) & ~3;
     if (s->n_slots > 0) {
         const int st = ensure_carry_ws(g, (size_t)s->n_slots * (size_t)ws_ld);
         if (st != SGLB200_OK) return st;
     }
-    SpmmParams p;
+    SpmmParams p = {};
     p.indptr = g->indptr;
     p.indices = g->indices;
-    p.vals = g->vals;
+    p.vals = raw_weights ? g->raw_w : g->vals;   // raw_w is NULL when every raw weight is 1
     p.tile_row = s->tile_row;
     p.tile_nnz = s->tile_nnz;
     p.carry_slot = s->carry_slot;
@@ -813,6 +780,25 @@ int spmm_launch_tiles(sglb200_graph *g, const float *X, int64_t ldx, float *Y, i
         }
         // one counter per cut row: valid while a tile is one participant, i.e. a single column block (d <= 512)
         p.fold = (fold_mode == 1 && s->n_runs > 0 && spmm_variant() < 10 && col_blocks == 1) ? 1 : 0;
+        if (p.fold) {
+            // the arrival counters assume that one hop's tile ranges are issued completely, in order, on one stream
+            // (include/sglb200.h, sglb200_spmm_tiles).  A hop that starts while an earlier one was left open (aborted
+            // between ranges) gets fresh counters; a hop on another stream first waits for the previous fold to finish.
+            if (s->next_tile != 0 && tile_begin != s->next_tile) {
+                SGL_REQUIRE(tile_begin == 0, "spmm_tiles: tile ranges of one hop must be issued in order (expected tile %lld, got %lld)",
+                            (long long)s->next_tile, (long long)tile_begin);
+                if (s->stream_known && s->last_stream != stream) SGL_CUDA_CHECK(cudaStreamSynchronize(s->last_stream));
+                SGL_CUDA_CHECK(cudaMemsetAsync(s->run_count, 0, sizeof(uint32_t) * (size_t)s->n_runs, stream));
+            } else if (s->stream_known && s->last_stream != stream) {
+                SGL_CUDA_CHECK(cudaStreamSynchronize(s->last_stream));   // rare: the previous hop's fold must have finished
+            }
+        }
+        if (epi) {
+            SGL_REQUIRE(s->n_runs == 0 || p.fold, "spmm: the fused row flush needs the in-kernel fold (d <= 512)");
+            SGL_REQUIRE(col_blocks == 1, "spmm: the fused row flush supports feature widths up to 512");
+            p.epi = *epi;
+            p.epi.active = 1;
+        }
         p.tail_run = s->tail_run;
         p.head_run = s->head_run;
         p.run_row = s->run_row;
@@ -838,6 +824,16 @@ int spmm_launch_tiles(sglb200_graph *g, const float *X, int64_t ldx, float *Y, i
 
     const dim3 grid((unsigned)((tile_end - tile_begin + kWarpsPerBlock - 1) / kWarpsPerBlock), (unsigned)col_blocks, 1);
     const bool acc = accumulate != 0;
+    // the flagged column stream (row ends carried by bit 31) where the graph allows it: no empty rows, ids below 2^30
+    const int32_t *tags = nullptr;
+    if (!acc && env_int("SGLB200_FLAGS", 1) != 0) {
+        if (g->empty_rows < 0) {
+            const int st = build_stream_tags(g, stream);
+            if (st != SGLB200_OK) return st;
+        }
+        if (g->empty_rows == 0 && g->n_cols < (1LL << 30)) tags = g->idx_tag;
+    }
+    g_flat_tags = tags;
     cudaError_t e = cudaSuccess;
 #define SGL_SHAPE(V, L, UU, MB) \
     if (vec == V && vpl == L) e = launch_flat<V, L, UU, MB>(p, acc, grid, stream)
@@ -870,15 +866,16 @@ int spmm_launch_tiles(sglb200_graph *g, const float *X, int64_t ldx, float *Y, i
         }
 #undef SGL_RING
     }
+    else if (use_tma) {
+        e = spmm_tma_launch(g, p, stream);
+    }
+    else if (use_groups) {
+        e = spmm_group_launch(p, acc, tags, stream);
+    }
     else if (vec == 4 && vpl == 1) {
         switch (variant) {
-        case 2: e = launch_flat<4, 1, 4, 4, 1>(p, acc, grid, stream); break;
         case 3: e = launch_flat<4, 1, 4, 3, 2>(p, acc, grid, stream); break;
-        case 4: e = launch_flat<4, 1, 4, 4, 2>(p, acc, grid, stream); break;
-        case 5: e = launch_flat<4, 1, 8, 4, 1>(p, acc, grid, stream); break;
-        case 6: e = launch_flat<4, 1, 2, 5, 2>(p, acc, grid, stream); break;
         case 7: e = launch_flat<4, 1, 8, 2, 2>(p, acc, grid, stream); break;
-        case 8: e = launch_flat<4, 1, 4, 5, 1>(p, acc, grid, stream); break;
         default: e = launch_flat<4, 1, 8, 3, 1>(p, acc, grid, stream); break;  // measured best on B200 (profiles/)
         }
     }
@@ -896,6 +893,11 @@ int spmm_launch_tiles(sglb200_graph *g, const float *X, int64_t ldx, float *Y, i
     }
 #undef SGL_SHAPE
     SGL_CUDA_CHECK(e);
+    if (p.fold) {
+        s->next_tile = tile_end >= s->n_tiles ? 0 : tile_end;
+        s->last_stream = stream;
+        s->stream_known = true;
+    }
     if (s->n_runs > 0 && !p.fold) {
         // runs are sorted by tile: those whose finishing tile lies in [tile_begin, tile_end) form one contiguous range
         const auto &last = s->run_last_tile;

@@ -1,0 +1,256 @@
+// spmm_group.cu -- the hop kernel for NARROW feature rows (d <= 64 floats): lane groups instead of whole warps.
+//
+// With d <= 64 a feature row is at most 16 float4 slices, so a 32-lane warp walking one tile (spmm.cu) idles half of its
+// lanes or more -- and narrow rows are exactly what the feature-split partition of the multi-GPU path produces (d / 8
+// columns per GPU) and what column-tiled hops use.  Here a warp is cut into 32 / G groups of G lanes
+// (G = 4, 8, 16); every group is a "virtual warp" that owns its OWN merge-path tile and walks it exactly like the
+// full-warp kernel does: flat (col, val) stream staged in shared memory, U gathered rows in flight, sequential fma
+// chain per output element in CSR order (=> the same bits as the reference's matmul.c:30-37 chain for rows that are not
+// cut), cut rows folded by the last arriver.  One warp-wide LDG.128 therefore fetches 32 / G different feature rows.
+// Control flow that is warp-uniform in spmm.cu (row ends, loop bounds) is group-uniform here: shuffles and barriers
+// name the group's lane mask only.
+#include <stdlib.h>
+
+#include "spmm_common.cuh"
+
+namespace sglb200 {
+
+// FLAG: the column stream is the tagged one (bit 31 = last non-zero of its row; graphs without empty rows): a row ends
+// where the stream says so, which turns the group-divergent row flush (window refill + shuffles) into a few predicated
+// instructions -- with 8 groups per warp the divergent flush was 70 % of the instruction stream.
+template <int G, int U, bool ACCUM, bool EPI = false, bool FLAG = false>
+__global__ void __launch_bounds__(kWarpsPerBlock * 32, G == 4 ? 2 : 3) spmm_group_kernel(const SpmmParams p, const int32_t *__restrict__ idx_tag)
+{
+    static_assert(!(FLAG && ACCUM), "the flagged walk starts every chain from zero");
+    static_assert(!(EPI && ACCUM), "the fused row flush starts every chain from zero");
+    constexpr int NG = 32 / G;   // tiles per warp
+    constexpr int R = 32 / G;    // (col, val) pairs each lane fetches per batch of 32
+    static_assert(G == 4 || G == 8 || G == 16, "group width");
+    static_assert(32 % U == 0, "U must divide the batch of 32 non-zeros");
+    __shared__ int2 s_pairs[kWarpsPerBlock][NG][64];
+    const int lane = threadIdx.x & 31;
+    const int gl = lane & (G - 1);   // lane inside the group
+    const int gid = lane / G;        // group inside the warp
+    const unsigned gmask = (G == 32 ? 0xffffffffu : ((1u << G) - 1u)) << (gid * G);
+    const int64_t t = p.tile_begin + ((int64_t)blockIdx.x * kWarpsPerBlock + (threadIdx.x >> 5)) * NG + gid;
+    if (t >= p.n_tiles) return;      // whole groups leave; nothing below synchronises beyond the group
+    int2 *pairs = &s_pairs[threadIdx.x >> 5][gid][0];
+
+    int row = p.tile_row[t];
+    const int row_end = p.tile_row[t + 1];
+    const int64_t j0 = p.tile_nnz[t];
+    const int n_nnz = (int)(p.tile_nnz[t + 1] - j0);
+    const int n_rows = (int)p.n_rows;
+
+    const int cofs = gl * 4;
+    const bool act = cofs < p.d;
+    const char *xbase = reinterpret_cast<const char *>(p.X) + (size_t)(act ? cofs : 0) * sizeof(float);
+    char *ybase = reinterpret_cast<char *>(p.Y) + (size_t)cofs * sizeof(float);
+    const uint32_t ldx_bytes = (uint32_t)p.ldx * (uint32_t)sizeof(float);
+    const uint32_t ldy_bytes = (uint32_t)p.ldy * (uint32_t)sizeof(float);
+    Slice<4> accs[1];
+    Slice<4> &acc = accs[0];
+    const bool acts[1] = {act};
+    const int cofss[1] = {cofs};
+    int cont_slot = -1;   // fused row flush: see spmm_flat_kernel
+    if constexpr (EPI) {
+        if (p.fold) {
+            const int hr = p.head_run[t];
+            if (hr >= 0) cont_slot = (int)(p.run_base[hr] + p.run_len[hr]);
+        }
+    }
+
+    auto init_acc = [&](int r) {
+        acc.zero();
+        if (ACCUM) {
+            if (act && r < n_rows) acc.load(ybase + (uint64_t)(uint32_t)r * ldy_bytes);
+        }
+    };
+    // ends (relative to j0) of rows row_base .. row_base+G-1, one per lane of the group
+    auto load_row_ends = [&](int base) -> int {
+        const int r = base + 1 + gl;
+        if (r > n_rows) return INT_MAX;
+        const int64_t rel = p.indptr[r] - j0;
+        return rel > (int64_t)INT_MAX ? INT_MAX : (int)rel;
+    };
+    int row_base = row;
+    int my_end = FLAG ? 0 : load_row_ends(row_base);
+    int next_end = FLAG ? 0 : __shfl_sync(gmask, my_end, 0, G);
+    if (row >= row_end) next_end = INT_MAX;
+    if (ACCUM) {
+        const bool starts_here = row < n_rows && p.indptr[row] == j0;
+        init_acc(starts_here ? row : n_rows);
+    } else {
+        init_acc(n_rows);
+    }
+    auto flush_row = [&]() {
+        if constexpr (EPI) {
+            if (cont_slot >= 0) {
+                if (act) acc.store(reinterpret_cast<char *>(p.carry_ws + (int64_t)cont_slot * p.ws_ld) + (size_t)cofs * sizeof(float));
+                cont_slot = -1;
+            } else {
+                emit_row<4, 1, G>(p, (uint32_t)row, accs, acts, cofss, gmask);
+            }
+        } else if (act) {
+            if (p.stream_y) acc.store_streaming(ybase + (uint64_t)(uint32_t)row * ldy_bytes);
+            else acc.store(ybase + (uint64_t)(uint32_t)row * ldy_bytes);
+        }
+        ++row;
+        if constexpr (!FLAG) {
+            if (row - row_base == G) {
+                row_base = row;
+                my_end = load_row_ends(row_base);
+            }
+            const int e = __shfl_sync(gmask, my_end, row - row_base, G);
+            next_end = row < row_end ? e : INT_MAX;
+        }
+        init_acc(row);
+    };
+
+    if constexpr (FLAG) {
+        // the one row a flag cannot retire: a cut row whose non-zeros all lie in earlier tiles (the boundary fell between
+        // its last non-zero and its end marker) -- this tile finishes it with an empty piece
+        if (row < row_end && p.indptr[row + 1] == j0) flush_row();
+    }
+    const int32_t *cols = (FLAG ? idx_tag : p.indices) + j0;
+    const float *vals = p.vals + j0;
+    // every lane of the group fetches R of the next 32 (col, val) pairs (interleaved: the group reads G consecutive
+    // elements per instruction), one batch ahead of their publication
+    int32_t col_next[R];
+    float val_next[R];
+    auto fetch_batch = [&](int b) {
+#pragma unroll
+        for (int i = 0; i < R; ++i) {
+            const int nb = b * 32 + i * G + gl;
+            col_next[i] = 0;
+            val_next[i] = 0.0f;
+            if (nb < n_nnz) {
+                col_next[i] = __ldg(cols + nb);
+                val_next[i] = p.vals ? __ldg(vals + nb) : 1.0f;
+            }
+        }
+    };
+    fetch_batch(0);
+    auto publish_batch = [&](int b) {
+        __syncwarp(gmask);  // the group is done with the batch that used this buffer two batches ago
+#pragma unroll
+        for (int i = 0; i < R; ++i) pairs[(b & 1) * 32 + i * G + gl] = make_int2(col_next[i], __float_as_int(val_next[i]));
+        __syncwarp(gmask);
+        fetch_batch(b + 1);
+    };
+
+    const int n_groups = (n_nnz + U - 1) / U;
+#pragma unroll 1
+    for (int g = 0; g < n_groups; ++g) {
+        const int pos = g * U;
+        if ((pos & 31) == 0) publish_batch(pos >> 5);
+        const int2 *pp = pairs + (pos & 63);
+        Slice<4> buf[U];
+#pragma unroll
+        for (int u = 0; u < U; ++u) buf[u].load_nc(xbase + (uint64_t)((uint32_t)pp[u].x & (FLAG ? 0x3fffffffu : 0xffffffffu)) * ldx_bytes);
+        const int valid = n_nnz - pos;
+        if constexpr (FLAG) {
+#pragma unroll
+            for (int u = 0; u < U; ++u) {
+                const int2 cw = pp[u];
+                if (u < valid) {
+                    acc.fma(__int_as_float(cw.y), buf[u]);
+                    if (cw.x < 0 && row < row_end) flush_row();
+                }
+            }
+        } else {
+            int left = next_end - pos;
+#pragma unroll
+            for (int u = 0; u < U; ++u) {
+                const float w = __int_as_float(pp[u].y);
+                while (u == left) {  // group-uniform: the current row ends here (also retires empty rows)
+                    flush_row();
+                    left = next_end - pos;
+                }
+                if (u < valid) acc.fma(w, buf[u]);
+            }
+        }
+    }
+    while (row < row_end) flush_row();
+    const int32_t slot = p.carry_slot[t];
+    if (slot >= 0 && act) {
+        char *wrow = reinterpret_cast<char *>(p.carry_ws + (int64_t)slot * p.ws_ld);
+        acc.store(wrow + (size_t)cofs * sizeof(float));
+    }
+    // in-kernel fold of cut rows, as in spmm_flat_kernel, one group per participant
+    if (p.fold) {
+        const int finishes = p.head_run[t];
+        const int carries = slot >= 0 ? p.tail_run[t] : -1;
+        if (finishes >= 0 || carries >= 0) {
+            __threadfence();
+            __syncwarp(gmask);
+#pragma unroll 1
+            for (int role = 0; role < 2; ++role) {
+                const int run = role == 0 ? finishes : carries;
+                if (run < 0) continue;
+                const int n_carriers = p.run_len[run];
+                unsigned int seen = 0;
+                if (gl == 0) seen = atomicAdd(p.run_count + run, 1u);
+                seen = __shfl_sync(gmask, seen, 0, G);
+                if (seen != (unsigned int)n_carriers) continue;
+                __threadfence();
+                if constexpr (EPI) {
+                    const char *ws0 = reinterpret_cast<const char *>(p.carry_ws + p.run_base[run] * p.ws_ld);
+                    const size_t ws_ld_bytes = (size_t)p.ws_ld * sizeof(float);
+                    const size_t cb = (size_t)cofs * sizeof(float);
+                    Slice<4> sums[1], part;
+                    sums[0].zero();
+                    if (act) {
+                        sums[0].load_l2(ws0 + cb);
+                        for (int u = 1; u <= n_carriers; ++u) {
+                            part.load_l2(ws0 + (size_t)u * ws_ld_bytes + cb);
+                            sums[0].add(part);
+                        }
+                    }
+                    emit_row<4, 1, G>(p, (uint32_t)p.run_row[run], sums, acts, cofss, gmask);
+                } else if (act) {
+                    const char *ws0 = reinterpret_cast<const char *>(p.carry_ws + p.run_base[run] * p.ws_ld);
+                    const size_t ws_ld_bytes = (size_t)p.ws_ld * sizeof(float);
+                    const size_t cb = (size_t)cofs * sizeof(float);
+                    Slice<4> sum, part;
+                    sum.load_l2(ws0 + cb);
+                    for (int u = 1; u < n_carriers; ++u) {
+                        part.load_l2(ws0 + (size_t)u * ws_ld_bytes + cb);
+                        sum.add(part);
+                    }
+                    char *yp = ybase + (uint64_t)(uint32_t)p.run_row[run] * ldy_bytes;
+                    part.load_l2(yp);
+                    part.add(sum);
+                    part.store(yp);
+                }
+                if (gl == 0) p.run_count[run] = 0u;
+            }
+        }
+    }
+}
+
+template <int G, int U>
+static cudaError_t launch_group(const SpmmParams &p, bool accum, const int32_t *idx_tag, cudaStream_t stream)
+{
+    constexpr int NG = 32 / G;
+    const int64_t tiles = p.n_tiles - p.tile_begin;
+    const unsigned blocks = (unsigned)((tiles + (int64_t)kWarpsPerBlock * NG - 1) / ((int64_t)kWarpsPerBlock * NG));
+    if (accum) spmm_group_kernel<G, U, true><<<blocks, kWarpsPerBlock * 32, 0, stream>>>(p, nullptr);
+    else if (p.epi.active && idx_tag) spmm_group_kernel<G, U, false, true, true><<<blocks, kWarpsPerBlock * 32, 0, stream>>>(p, idx_tag);
+    else if (p.epi.active) spmm_group_kernel<G, U, false, true><<<blocks, kWarpsPerBlock * 32, 0, stream>>>(p, nullptr);
+    else if (idx_tag) spmm_group_kernel<G, U, false, false, true><<<blocks, kWarpsPerBlock * 32, 0, stream>>>(p, idx_tag);
+    else spmm_group_kernel<G, U, false><<<blocks, kWarpsPerBlock * 32, 0, stream>>>(p, nullptr);
+    return cudaGetLastError();
+}
+
+// d <= 64, float4 rows: picks the narrowest group that holds a row
+// idx_tag: the flagged column stream (NULL: walk with row-pointer windows -- graphs with empty rows, accumulate)
+cudaError_t spmm_group_launch(const SpmmParams &p, bool accum, const int32_t *idx_tag, cudaStream_t stream)
+{
+    const int slices = (p.d + 3) / 4;
+    if (slices <= 4) return launch_group<4, 8>(p, accum, idx_tag, stream);
+    if (slices <= 8) return launch_group<8, 8>(p, accum, idx_tag, stream);
+    return launch_group<16, 8>(p, accum, idx_tag, stream);
+}
+
+}  // namespace sglb200

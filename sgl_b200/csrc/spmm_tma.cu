@@ -1,0 +1,347 @@
+// spmm_tma.cu -- the hop kernel with TMA staging (sm_100a): feature rows are gathered FOUR AT A TIME by the tensor-map
+// engine (cp.async.bulk.tensor.2d.tile::gather4 -> SASS UTMALDG) into a per-warp shared-memory ring, and the warp's
+// (column, value) stream arrives by 1-D bulk copies (cp.async.bulk -> UBLKCP); both complete on mbarriers.
+//
+// Why: one hop is a random gather of nnz feature rows (matmul.c:30-37 does it with one scalar chain per element on the
+// CPU).  The register-staged kernel (spmm.cu) keeps 24 warps x 8 rows = 80 KB of gathers in flight per SM and is
+// latency bound on HBM-resident graphs (ncu: every unit 45-60 % busy, 72 % long-scoreboard stalls).  Here the bytes in
+// flight live in shared memory: no registers are held while a row travels, one elected lane issues the copies for the
+// whole warp, and the ring (2 stages x 8 rows per warp, 24 warps per SM) doubles the rows in flight.
+//
+// Walk of a tile (one warp, persistent over tiles):
+//   * the tile's non-zeros [j0, j1) are consumed as a stream q = j - (j0 & ~3): 16-byte aligned chunks of 64 (column,
+//     value) pairs are bulk-copied into a double-buffered per-warp chunk ring (chunk c is refilled with c+2 once the
+//     last group that reads it has been consumed);
+//   * groups of 8 consecutive stream positions form one ring stage: lane 0 reads the 8 column ids from the chunk ring and
+//     issues two gather4 copies (4 rows each) onto the stage's mbarrier; group g+2 is issued right after group g has
+//     been consumed, so 8..16 rows are in flight per warp at any time;
+//   * column ids carry the row structure: bit 31 = "last non-zero of its row" (graphs without empty rows, which every
+//     normalised adjacency of the reference is: A+I has a full diagonal, utils.py:77), so a row ends where the stream
+//     says so -- no row-pointer window, no countdown;
+//   * per output element the additions still happen in CSR order, one fused multiply-add per term: the EXACT schedule
+//     reproduces the reference's chain bit for bit, exactly like the register-staged kernel.
+// Cut rows, the carry workspace, the in-kernel fold and the fused row flush (emit_row) are shared with spmm.cu.
+#include <cuda.h>
+#include <stdlib.h>
+
+#include "spmm_common.cuh"
+
+namespace sglb200 {
+
+constexpr int kTmaRows = 8;        // rows per ring stage (two gather4 copies)
+constexpr int kTmaStages = 2;
+constexpr int kChunk = 64;         // stream positions per index chunk
+constexpr uint32_t kColMask = 0x3fffffffu;
+
+__device__ __forceinline__ uint32_t smem_addr(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(uint32_t bar, int count)
+{
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count));
+}
+__device__ __forceinline__ void mbar_expect(uint32_t bar, uint32_t bytes)
+{
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity)
+{
+    uint32_t done = 0;
+    while (!done) {
+        asm volatile("{ .reg .pred p; mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2; selp.u32 %0, 1, 0, p; }"
+                     : "=r"(done) : "r"(bar), "r"(parity) : "memory");
+    }
+}
+__device__ __forceinline__ void bulk_load(uint32_t dst, const void *src, uint32_t bytes, uint32_t bar)
+{
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                 ::"r"(dst), "l"(src), "r"(bytes), "r"(bar) : "memory");
+}
+__device__ __forceinline__ void gather4(uint32_t dst, const CUtensorMap *map, uint32_t bar, int c0, int r0, int r1, int r2, int r3)
+{
+    asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.tile::gather4.mbarrier::complete_tx::bytes"
+                 " [%0], [%1, {%3, %4, %5, %6, %7}], [%2];"
+                 ::"r"(dst), "l"(map), "r"(bar), "r"(c0), "r"(r0), "r"(r1), "r"(r2), "r"(r3) : "memory");
+}
+
+// smem per warp: [ring: stages x 2 blocks x blk_bytes][cols: 2 x 64 u32][vals: 2 x 64 f32][4 mbarriers]
+template <bool EPI, bool UNITW>
+__global__ void __launch_bounds__(kWarpsPerBlock * 32) spmm_tma_kernel(const __grid_constant__ CUtensorMap xmap, const SpmmParams p,
+                                                                       const uint32_t *__restrict__ idx_tag, int blk_bytes,
+                                                                       int warp_bytes, int64_t total_warps)
+{
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    const int lane = threadIdx.x & 31;
+    const int wib = threadIdx.x >> 5;
+    unsigned char *wbase = smem_raw + (size_t)wib * warp_bytes;
+    const int ring_bytes = kTmaStages * 2 * blk_bytes;
+    uint32_t *s_cols = reinterpret_cast<uint32_t *>(wbase + ring_bytes);
+    float *s_vals = reinterpret_cast<float *>(wbase + ring_bytes + 2 * kChunk * 4);
+    uint64_t *bars = reinterpret_cast<uint64_t *>(wbase + ring_bytes + 4 * kChunk * 4);
+    const uint32_t ring_s = smem_addr(wbase);
+    const uint32_t cols_s = smem_addr(s_cols), vals_s = smem_addr(s_vals);
+    const uint32_t bar_full0 = smem_addr(bars), bar_idx0 = smem_addr(bars + 2);
+    if (lane == 0) {
+        mbar_init(bar_full0, 1);
+        mbar_init(bar_full0 + 8, 1);
+        mbar_init(bar_idx0, 1);
+        mbar_init(bar_idx0 + 8, 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    __syncwarp();
+    uint32_t full_phase = 0, idx_phase = 0;   // bit s = parity the next wait on barrier s expects
+
+    const int row_bytes = p.d * 4;
+    const int cofs1[1] = {lane * 4};
+    const bool act1[1] = {lane * 4 < p.d};
+    const int lane_ofs = act1[0] ? lane * 16 : 0;   // idle lanes re-read slice 0 (never stored)
+    const int n_rows = (int)p.n_rows;
+
+#pragma unroll 1
+    for (int64_t t = p.tile_begin + (int64_t)blockIdx.x * kWarpsPerBlock + wib; t < p.n_tiles; t += total_warps) {
+        int row = p.tile_row[t];
+        const int row_end = p.tile_row[t + 1];
+        const int64_t j0 = p.tile_nnz[t];
+        const int n_nnz = (int)(p.tile_nnz[t + 1] - j0);
+        const int64_t a0 = j0 & ~(int64_t)3;          // 16-byte aligned start of the stream
+        const int off = (int)(j0 - a0);
+        const int q_end = off + n_nnz;                 // stream positions [off, q_end) are this tile's non-zeros
+        const int n_groups = n_nnz > 0 ? (q_end + kTmaRows - 1) / kTmaRows : 0;
+        const int n_chunks = n_nnz > 0 ? (q_end + kChunk - 1) / kChunk : 0;
+        int cont_slot = -1;
+        if constexpr (EPI) {
+            if (p.fold) {
+                const int hr = p.head_run[t];
+                if (hr >= 0) cont_slot = (int)(p.run_base[hr] + p.run_len[hr]);
+            }
+        }
+        Slice<4> acc[1];
+        acc[0].zero();
+
+        auto load_chunk = [&](int c) {   // lane 0 only
+            const uint32_t b = (uint32_t)(c & 1);
+            const uint32_t bar = bar_idx0 + 8 * b;
+            mbar_expect(bar, UNITW ? kChunk * 4 : kChunk * 8);
+            bulk_load(cols_s + b * kChunk * 4, idx_tag + a0 + (int64_t)c * kChunk, kChunk * 4, bar);
+            if (!UNITW) bulk_load(vals_s + b * kChunk * 4, p.vals + a0 + (int64_t)c * kChunk, kChunk * 4, bar);
+        };
+        auto issue_group = [&](int g) {  // lane 0 only; the chunk holding group g has landed (waited by the caller)
+            const uint32_t s = (uint32_t)(g & 1);
+            const uint32_t bar = bar_full0 + 8 * s;
+            const uint4 c0 = *reinterpret_cast<const uint4 *>(s_cols + ((g * kTmaRows) & (2 * kChunk - 1)));
+            const uint4 c1 = *reinterpret_cast<const uint4 *>(s_cols + ((g * kTmaRows + 4) & (2 * kChunk - 1)));
+            mbar_expect(bar, (uint32_t)(kTmaRows * row_bytes));
+            const uint32_t dst = ring_s + s * 2 * blk_bytes;
+            gather4(dst, &xmap, bar, 0, (int)(c0.x & kColMask), (int)(c0.y & kColMask), (int)(c0.z & kColMask), (int)(c0.w & kColMask));
+            gather4(dst + blk_bytes, &xmap, bar, 0, (int)(c1.x & kColMask), (int)(c1.y & kColMask), (int)(c1.z & kColMask),
+                    (int)(c1.w & kColMask));
+        };
+        auto flush_row = [&]() {
+            if constexpr (EPI) {
+                if (cont_slot >= 0) {
+                    if (act1[0]) acc[0].store(reinterpret_cast<char *>(p.carry_ws + (int64_t)cont_slot * p.ws_ld) + lane * 16);
+                    cont_slot = -1;
+                } else {
+                    emit_row<4, 1, 32>(p, (uint32_t)row, acc, act1, cofs1, kFull);
+                }
+            } else if (act1[0]) {
+                char *yp = reinterpret_cast<char *>(p.Y + (size_t)row * p.ldy) + lane * 16;
+                if (p.stream_y) acc[0].store_streaming(yp);
+                else acc[0].store(yp);
+            }
+            ++row;
+            acc[0].zero();
+        };
+
+        // the one row a flag cannot retire: a cut row whose non-zeros all lie in earlier tiles (the boundary fell between
+        // its last non-zero and its end marker) -- this tile finishes it with an empty piece
+        if (row < row_end && p.indptr[row + 1] == j0) flush_row();
+        // prologue: first two chunks, first two groups
+        int chunks_loaded = 0, chunks_ready = 0;
+        if (n_chunks > 0) {
+            if (lane == 0) {
+                load_chunk(0);
+                if (n_chunks > 1) load_chunk(1);
+            }
+            chunks_loaded = n_chunks > 1 ? 2 : 1;
+        }
+        if (n_groups > 0) {
+            mbar_wait(bar_idx0, idx_phase & 1u);
+            idx_phase ^= 1u;
+            chunks_ready = 1;
+            if (lane == 0) {
+                issue_group(0);
+                if (n_groups > 1) issue_group(1);   // group 1 lies in chunk 0 (8 < 64)
+            }
+        }
+#pragma unroll 1
+        for (int g = 0; g < n_groups; ++g) {
+            const uint32_t s = (uint32_t)(g & 1);
+            mbar_wait(bar_full0 + 8 * s, (full_phase >> s) & 1u);
+            full_phase ^= 1u << s;
+            const unsigned char *stage = wbase + s * 2 * blk_bytes + lane_ofs;
+            const int qb = g * kTmaRows;
+            const uint32_t *cp = s_cols + (qb & (2 * kChunk - 1));
+            const float *vp = s_vals + (qb & (2 * kChunk - 1));
+#pragma unroll
+            for (int u = 0; u < kTmaRows; ++u) {
+                Slice<4> x;
+                x.load(reinterpret_cast<const char *>(stage + (u >> 2) * blk_bytes + (u & 3) * row_bytes));
+                const uint32_t tag = cp[u];
+                const float w = UNITW ? 1.0f : vp[u];
+                const int q = qb + u;
+                if (q >= off && q < q_end) {       // warp-uniform
+                    acc[0].fma(w, x);
+                    if ((tag >> 31) && row < row_end) flush_row();
+                }
+            }
+            __syncwarp();   // everyone is done with stage s and with the chunk positions of group g
+            // refill: the chunk that group g closed (its last group) can take chunk c+2; then group g+2 goes into stage s
+            if (((qb + kTmaRows) & (kChunk - 1)) == 0) {
+                const int c_done = qb / kChunk;
+                if (c_done + 2 < n_chunks) {
+                    if (lane == 0) load_chunk(c_done + 2);
+                    chunks_loaded = c_done + 3;
+                }
+            }
+            if (g + 2 < n_groups) {
+                const int c_need = ((g + 2) * kTmaRows) / kChunk;
+                if (c_need >= chunks_ready) {       // first group of a chunk: wait for the chunk (warp-uniform)
+                    mbar_wait(bar_idx0 + 8 * (c_need & 1), (idx_phase >> (c_need & 1)) & 1u);
+                    idx_phase ^= 1u << (c_need & 1);
+                    chunks_ready = c_need + 1;
+                }
+                if (lane == 0) issue_group(g + 2);
+            }
+        }
+        // a tile with a single chunk pair may leave chunk 1 loaded but never waited for: drain it so that the barrier
+        // phases stay in step with idx_phase
+        while (chunks_ready < chunks_loaded) {
+            mbar_wait(bar_idx0 + 8 * (chunks_ready & 1), (idx_phase >> (chunks_ready & 1)) & 1u);
+            idx_phase ^= 1u << (chunks_ready & 1);
+            ++chunks_ready;
+        }
+        const int32_t slot = p.carry_slot[t];
+        if (slot >= 0 && act1[0])
+            acc[0].store(reinterpret_cast<char *>(p.carry_ws + (int64_t)slot * p.ws_ld) + lane * 16);
+        if (p.fold) {
+            const int finishes = p.head_run[t];
+            const int carries = slot >= 0 ? p.tail_run[t] : -1;
+            if (finishes >= 0 || carries >= 0) {
+                __threadfence();
+                __syncwarp();
+#pragma unroll 1
+                for (int role = 0; role < 2; ++role) {
+                    const int run = role == 0 ? finishes : carries;
+                    if (run < 0) continue;
+                    const int n_carriers = p.run_len[run];
+                    unsigned int seen = 0;
+                    if (lane == 0) seen = atomicAdd(p.run_count + run, 1u);
+                    seen = __shfl_sync(kFull, seen, 0);
+                    if (seen != (unsigned int)n_carriers) continue;
+                    __threadfence();
+                    const char *ws0 = reinterpret_cast<const char *>(p.carry_ws + p.run_base[run] * p.ws_ld) + lane * 16;
+                    const size_t ws_ld_bytes = (size_t)p.ws_ld * sizeof(float);
+                    const uint32_t out_row = (uint32_t)p.run_row[run];
+                    Slice<4> sum[1], part;
+                    sum[0].zero();
+                    if constexpr (EPI) {
+                        if (act1[0]) {
+                            sum[0].load_l2(ws0);
+                            for (int u = 1; u <= n_carriers; ++u) {
+                                part.load_l2(ws0 + (size_t)u * ws_ld_bytes);
+                                sum[0].add(part);
+                            }
+                        }
+                        emit_row<4, 1, 32>(p, out_row, sum, act1, cofs1, kFull);
+                    } else if (act1[0]) {
+                        sum[0].load_l2(ws0);
+                        for (int u = 1; u < n_carriers; ++u) {
+                            part.load_l2(ws0 + (size_t)u * ws_ld_bytes);
+                            sum[0].add(part);
+                        }
+                        char *yp = reinterpret_cast<char *>(p.Y + (size_t)out_row * p.ldy) + lane * 16;
+                        part.load_l2(yp);
+                        part.add(sum[0]);
+                        part.store(yp);
+                    }
+                    if (lane == 0) p.run_count[run] = 0u;
+                }
+            }
+        }
+        (void)n_rows;
+    }
+}
+
+typedef CUresult (*EncodeTiledFn)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *, const cuuint64_t *, const cuuint64_t *,
+                                  const cuuint32_t *, const cuuint32_t *, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+static EncodeTiledFn encode_fn()
+{
+    static EncodeTiledFn fn = nullptr;
+    static bool tried = false;
+    if (!tried) {
+        tried = true;
+        void *f = nullptr;
+        cudaDriverEntryPointQueryResult q;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &f, cudaEnableDefault, &q) == cudaSuccess &&
+            q == cudaDriverEntryPointSuccess)
+            fn = (EncodeTiledFn)f;
+        (void)cudaGetLastError();
+    }
+    return fn;
+}
+
+// true when the TMA kernel can run this hop (the caller falls back to the register-staged kernels otherwise)
+bool spmm_tma_eligible(const sglb200_graph *g, const float *X, int64_t ldx, int d)
+{
+    return g->idx_tag != nullptr && g->empty_rows == 0 && g->n_cols < (1LL << 30) && d % 4 == 0 && d >= 4 && d <= 128 &&
+           ldx % 4 == 0 && (reinterpret_cast<uintptr_t>(X) & 15) == 0 && encode_fn() != nullptr;
+}
+
+cudaError_t spmm_tma_launch(const sglb200_graph *g, const SpmmParams &p, cudaStream_t stream)
+{
+    CUtensorMap map;
+    const cuuint64_t dims[2] = {(cuuint64_t)p.d, (cuuint64_t)g->n_cols};
+    const cuuint64_t strides[1] = {(cuuint64_t)p.ldx * 4};
+    const cuuint32_t box[2] = {(cuuint32_t)p.d, 1};
+    const cuuint32_t estr[2] = {1, 1};
+    const CUresult r = encode_fn()(&map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<float *>(p.X), dims, strides, box, estr,
+                                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_NONE,
+                                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) return cudaErrorInvalidValue;
+    const int row_bytes = p.d * 4;
+    const int blk_bytes = ((4 * row_bytes + 127) / 128) * 128;            // one gather4 destination, 128-byte aligned
+    const int warp_bytes = ((kTmaStages * 2 * blk_bytes + 4 * kChunk * 4 + 4 * 8 + 127) / 128) * 128;
+    const int cta_bytes = kWarpsPerBlock * warp_bytes;
+    const int64_t tiles = p.n_tiles - p.tile_begin;
+    int ctas_per_sm = (227 * 1024) / (cta_bytes + 1024);
+    if (ctas_per_sm < 1) return cudaErrorInvalidConfiguration;
+    if (ctas_per_sm > 4) ctas_per_sm = 4;
+    int64_t blocks = (int64_t)g->sm_count * ctas_per_sm;
+    const int64_t needed = (tiles + kWarpsPerBlock - 1) / kWarpsPerBlock;
+    if (blocks > needed) blocks = needed;
+    const int64_t total_warps = blocks * kWarpsPerBlock;
+    const bool unitw = p.vals == nullptr;
+#define TMA_GO(E, W)                                                                                                   \
+    do {                                                                                                               \
+        static int attr_bytes = 0;                                                                                     \
+        if (attr_bytes < cta_bytes) {                                                                                  \
+            cudaError_t e = cudaFuncSetAttribute(spmm_tma_kernel<E, W>, cudaFuncAttributeMaxDynamicSharedMemorySize, cta_bytes); \
+            if (e != cudaSuccess) return e;                                                                            \
+            attr_bytes = cta_bytes;                                                                                    \
+        }                                                                                                              \
+        spmm_tma_kernel<E, W><<<(unsigned)blocks, kWarpsPerBlock * 32, cta_bytes, stream>>>(                           \
+            map, p, reinterpret_cast<const uint32_t *>(g->idx_tag), blk_bytes, warp_bytes, total_warps);               \
+    } while (0)
+    if (p.epi.active) {
+        if (unitw) TMA_GO(true, true);
+        else TMA_GO(true, false);
+    } else {
+        if (unitw) TMA_GO(false, true);
+        else TMA_GO(false, false);
+    }
+#undef TMA_GO
+    return cudaGetLastError();
+}
+
+}  // namespace sglb200

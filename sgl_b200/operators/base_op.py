@@ -16,11 +16,29 @@ from torch import Tensor
 from ..runtime import CsrOperator, require_cuda
 
 
+def adjacency_fingerprint(adj):
+    """Cheap identity of a scipy CSR adjacency: shape, nnz, buffer addresses and a strided checksum of the three arrays.
+    Lets repeated propagate() calls on the same matrix reuse the resident operator (the reference rebuilds A^ on every
+    call, base_op.py:20; its label-use task calls preprocess every epoch) while an in-place edit of adj.data, which
+    keeps the object identity, still invalidates it."""
+    def probe(a):
+        a = np.asarray(a)
+        step = max(1, a.size // 4096)
+        return (a.ctypes.data, a.size, a.dtype.str, float(np.asarray(a[::step], dtype=np.float64).sum()),
+                float(a[-1]) if a.size else 0.0)
+    return (tuple(adj.shape), int(adj.nnz), probe(adj.data), probe(adj.indices), probe(adj.indptr))
+
+
 def propagate_reference_contract(op, adj, feature):
     """The body of GraphOp.propagate with the reference's exact contract (base_op.py:19-36): build A^ with the
     operator's own `_construct_adj`, validate, run the K hops on the GPU.  `op` may be one of our GraphOp objects or an
     instance of the reference's own classes (sgl_b200.patch binds this function to sgl.operators.base_op.GraphOp)."""
-    op._adj = op._construct_adj(adj)
+    fingerprint = adjacency_fingerprint(adj) if isinstance(adj, sp.csr_matrix) else None
+    cached = getattr(op, "_sglb200_cached", None)
+    reuse = fingerprint is not None and cached is not None and cached[0] == fingerprint \
+        and getattr(op, "_operator", None) is not None and getattr(op._operator, "_h", None)
+    if not reuse:
+        op._adj = op._construct_adj(adj)
 
     if not isinstance(adj, sp.csr_matrix):
         raise TypeError("The adjacency matrix must be a scipy csr sparse matrix!")
@@ -39,10 +57,12 @@ def propagate_reference_contract(op, adj, feature):
         first = torch.from_numpy(feature)  # shares memory, like torch.FloatTensor(ndarray) at base_op.py:36
     require_cuda()
 
-    previous = getattr(op, "_operator", None)
-    if previous is not None:
-        previous.close()
-    op._operator = CsrOperator.from_scipy(op._adj)
+    if not reuse:
+        previous = getattr(op, "_operator", None)
+        if previous is not None:
+            previous.close()
+        op._operator = CsrOperator.from_scipy(op._adj)
+        op._sglb200_cached = (fingerprint,)
     mode = getattr(op, "mode", "fast")
     steps = op._prop_steps
     if getattr(op, "output_device", "cpu") == "cuda":
@@ -117,6 +137,7 @@ class GraphOp:
             self._adj = self._construct_adj(adj)
             self._operator = CsrOperator.from_scipy(self._adj)
         self._prepared_for = adj
+        self._prepared_print = adjacency_fingerprint(adj) if isinstance(adj, sp.csr_matrix) else None
         return self
 
     def propagate_device(self, adj, feature, concat=False):
@@ -133,6 +154,22 @@ class GraphOp:
         x = feature.detach().to(dtype=torch.float32).to(self._operator.device, non_blocking=True)
         return self._operator.propagate(x, self._prop_steps, mode=self.mode, concat=concat)
 
+    def propagate_aggregate_device(self, adj, feature, spec, keep="none"):
+        """propagate + aggregate in one pass per hop (sglb200_propagate_fused): `spec` is a MessageOp.fused_spec() dict.
+        Returns (hops, out) as CUDA tensors; hops[k] is None where hop k was not stored."""
+        if getattr(self, "_prepared_for", None) is not adj or self._operator is None:
+            self.prepare(adj)
+        if feature.shape[0] != self._operator.shape[1]:
+            raise ValueError("Dimension mismatch detected for the adjacency and the feature matrix!")
+        if isinstance(feature, np.ndarray):
+            if feature.dtype != np.float32:
+                raise TypeError("The feature matrix must be a float32 numpy.ndarray!")
+            feature = torch.from_numpy(feature)
+        x = feature.detach().to(dtype=torch.float32).to(self._operator.device, non_blocking=True)
+        return self._operator.propagate_fused(x, self._prop_steps, mode=self.mode, keep=keep, agg=spec.get("agg"),
+                                              start=spec.get("start", 0), end=spec.get("end"),
+                                              weights=spec.get("weights"))
+
     def propagate(self, adj, feature):
         if self.cache_dir and isinstance(adj, sp.csr_matrix) and isinstance(feature, (np.ndarray, Tensor)) \
                 and adj.shape[1] == feature.shape[0]:
@@ -142,11 +179,19 @@ class GraphOp:
     def _propagate_cached(self, adj, feature):
         from ..cache import HopCache
         spec = self._norm_spec()
-        params = {"r": spec[0], "alpha": spec[1]} if spec is not None else {}
+        if spec is not None:
+            params = {"r": spec[0], "alpha": spec[1]}
+        elif hasattr(self, "cache_params"):
+            params = dict(self.cache_params())
+        else:
+            # a user-defined operator without declared hyper-parameters: its A^ cannot be keyed safely
+            return self._propagate_uncached(adj, feature)
         cache = HopCache(self.cache_dir)
         key = cache.key(adj, feature, type(self).__name__ + ":" + self.mode, self._prop_steps, **params)
         hops = cache.load(key)
         if hops is not None:
+            if self._adj_value is None and self._adj_parts is None:
+                self._adj = self._construct_adj(adj)   # the reference contract: _adj is set after propagate (base_op.py:20)
             first = torch.from_numpy(feature) if isinstance(feature, np.ndarray) else feature.detach().float().cpu()
             hops = [first] + hops[1:]
             return [h.cuda() for h in hops] if self.output_device == "cuda" else hops
@@ -156,6 +201,7 @@ class GraphOp:
 
     def _propagate_uncached(self, adj, feature):
         if getattr(self, "_prepared_for", None) is adj and self._operator is not None \
+                and getattr(self, "_prepared_print", None) == adjacency_fingerprint(adj) \
                 and isinstance(feature, (np.ndarray, Tensor)) and feature.shape[0] == self._operator.shape[1]:
             hops = self.propagate_device(adj, feature)
             if self.output_device == "cuda":

@@ -16,7 +16,34 @@ from ...runtime import aggregate, require_cuda
 from ..base_op import MessageOp
 
 
+def _needs_autograd(feats) -> bool:
+    """The kernels are forward-only: inputs that carry gradients (a learnable aggregator upstream, reference
+    models/base_model.py:119-222) are combined with the reference's own differentiable torch expressions instead."""
+    return torch.is_grad_enabled() and any(isinstance(f, Tensor) and f.requires_grad for f in feats)
+
+
+def _torch_combine(op: int, feats, weights=None) -> Tensor:
+    if op == _lib.AGG_SUM:
+        return sum(feats)
+    if op == _lib.AGG_MEAN:
+        return sum(feats) / len(feats)
+    if op == _lib.AGG_MAX:
+        return torch.stack(feats, dim=0).max(dim=0)[0]
+    if op == _lib.AGG_MIN:
+        return torch.stack(feats, dim=0).min(dim=0)[0]
+    if op == _lib.AGG_CONCAT:
+        return torch.hstack(feats)
+    if op == _lib.AGG_WEIGHTED:
+        return sum(f * float(w) for f, w in zip(feats, weights))
+    x = feats[0]
+    cos = [(x * f).sum(1) / (f.norm(dim=1) + 1e-10) / (x.norm(dim=1) + 1e-10) for f in feats]
+    w = torch.softmax(torch.stack(cos, dim=1), dim=1)
+    return sum(f * w[:, k:k + 1] for k, f in enumerate(feats))
+
+
 def _run(op: int, feats, weights=None) -> Tensor:
+    if _needs_autograd(feats):
+        return _torch_combine(op, list(feats), weights)
     require_cuda()
     on_cpu = not feats[0].is_cuda
     dev_feats, _ = _u._to_cuda(list(feats))
@@ -34,6 +61,10 @@ class LastMessageOp(MessageOp):
     def _combine(self, feat_list):
         return feat_list[-1]
 
+    def fused_spec(self, prop_steps):
+        """How sglb200_propagate_fused folds this combiner into the hop kernels (None: not fusable)."""
+        return {"agg": "last"}
+
 
 class SumMessageOp(MessageOp):
     """Left-to-right float32 sum of hops [start, end) (reference sum_message_op.py:4-10)."""
@@ -44,6 +75,11 @@ class SumMessageOp(MessageOp):
 
     def _combine(self, feat_list):
         return _run(_lib.AGG_SUM, feat_list[self._start:self._end])
+
+    def fused_spec(self, prop_steps):
+        if not (0 <= self._start < self._end <= prop_steps + 1):
+            return None
+        return {"agg": "sum", "start": self._start, "end": self._end}
 
 
 class MeanMessageOp(MessageOp):
@@ -60,6 +96,11 @@ class MeanMessageOp(MessageOp):
             return _run(_lib.AGG_SUM, sel) / (self._end - self._start)
         return _run(_lib.AGG_MEAN, sel)
 
+    def fused_spec(self, prop_steps):
+        if not (0 <= self._start < self._end <= prop_steps + 1):
+            return None
+        return {"agg": "mean", "start": self._start, "end": self._end}
+
 
 class MaxMessageOp(MessageOp):
     """Element-wise maximum over hops [start, end) (reference max_message_op.py:6-12)."""
@@ -70,6 +111,11 @@ class MaxMessageOp(MessageOp):
 
     def _combine(self, feat_list):
         return _run(_lib.AGG_MAX, feat_list[self._start:self._end])
+
+    def fused_spec(self, prop_steps):
+        if not (0 <= self._start < self._end <= prop_steps + 1):
+            return None
+        return {"agg": "max", "start": self._start, "end": self._end}
 
 
 class MinMessageOp(MessageOp):
@@ -82,6 +128,11 @@ class MinMessageOp(MessageOp):
     def _combine(self, feat_list):
         return _run(_lib.AGG_MIN, feat_list[self._start:self._end])
 
+    def fused_spec(self, prop_steps):
+        if not (0 <= self._start < self._end <= prop_steps + 1):
+            return None
+        return {"agg": "min", "start": self._start, "end": self._end}
+
 
 class ConcatMessageOp(MessageOp):
     """[N, (end-start)*d] horizontal stack of hops [start, end) (reference concat_message_op.py:6-12)."""
@@ -92,6 +143,11 @@ class ConcatMessageOp(MessageOp):
 
     def _combine(self, feat_list):
         return _run(_lib.AGG_CONCAT, feat_list[self._start:self._end])
+
+    def fused_spec(self, prop_steps):
+        if not (0 <= self._start < self._end <= prop_steps + 1):
+            return None
+        return {"agg": "concat", "start": self._start, "end": self._end}
 
 
 class SimpleWeightedMessageOp(MessageOp):
@@ -134,6 +190,21 @@ class SimpleWeightedMessageOp(MessageOp):
             self._weight_list = torch.FloatTensor(weights[self._start:self._end])
         return _u.one_dim_weighted_add(feat_list[self._start:self._end], weight_list=self._weight_list)
 
+    def fused_spec(self, prop_steps):
+        if not (0 <= self._start < self._end <= prop_steps + 1):
+            return None
+        if self._combination_type == "alpha":
+            weights = [self._alpha]
+            for _ in range(prop_steps):
+                weights.append((1 - self._alpha) * weights[-1])
+            per_hop = [float(v) for v in torch.FloatTensor(weights)]
+        else:
+            wl = [float(v) for v in self._weight_list]
+            if len(wl) != self._end - self._start:
+                return None
+            per_hop = [0.0] * self._start + wl + [0.0] * (prop_steps + 1 - self._end)
+        return {"agg": "weighted", "start": self._start, "end": self._end, "weights": per_hop}
+
 
 class OverSmoothDistanceWeightedOp(MessageOp):
     """NAFS hop weights: softmax over hops of the cosine between a node's raw and smoothed features
@@ -145,3 +216,6 @@ class OverSmoothDistanceWeightedOp(MessageOp):
 
     def _combine(self, feat_list):
         return _run(_lib.AGG_OSD, feat_list)
+
+    def fused_spec(self, prop_steps):
+        return {"agg": "osd"}

@@ -201,6 +201,56 @@ class CsrOperator:
                                                 _MODES[mode], _stream_ptr()), "propagate")
         return hops
 
+    # ---- K hops + degree normalisation + cross-hop aggregation in one pass per hop -----------------------------
+    def propagate_fused(self, x: torch.Tensor, prop_steps: int, mode="fast", keep="none", agg: Optional[str] = None,
+                        start: int = 0, end: Optional[int] = None, weights=None, fuse_norm: bool = True):
+        """K hops through sglb200_propagate_fused.  keep: "none" | "last" | "all" -- which hops are stored;
+        agg: None | "sum" | "mean" | "max" | "min" | "weighted" | "concat" | "osd" | "last" over hops [start, end)
+        (reference message_op/*.py; weights: one float per hop 0..K for "weighted").  Returns (hops, out): hops is a list
+        of K+1 entries (None where a hop was not stored; entry 0 is x), out the aggregate or None.
+        With fuse_norm and FAST mode on an operator built by sgl_b200.graph_build the normalised values are never read:
+        the kernel streams the raw weights and applies deg^(r-1) / deg^(-r) in the row flush."""
+        if self.shape[0] != self.shape[1]:
+            raise ValueError("propagate needs a square operator")
+        if not (isinstance(x, torch.Tensor) and x.is_cuda and x.dtype == torch.float32 and x.dim() == 2):
+            raise TypeError("propagate_fused: x must be a 2-D CUDA float32 tensor")
+        n, d = int(x.shape[0]), int(x.shape[1])
+        if n != self.shape[1]:
+            raise ValueError("Dimension mismatch detected for the adjacency and the feature matrix!")
+        if x.stride(1) != 1:
+            x = x.contiguous()
+        K = int(prop_steps)
+        end = K + 1 if end is None else int(end)
+        ops = {None: -1, "sum": _lib.AGG_SUM, "mean": _lib.AGG_MEAN, "max": _lib.AGG_MAX, "min": _lib.AGG_MIN,
+               "weighted": _lib.AGG_WEIGHTED, "concat": _lib.AGG_CONCAT, "osd": _lib.AGG_OSD, "last": _lib.AGG_LAST}
+        if agg not in ops:
+            raise ValueError(f"unknown aggregation {agg!r}")
+        hops: List[Optional[torch.Tensor]] = [x] + [None] * K
+        if keep == "all":
+            hops = [x] + [torch.empty((n, d), dtype=torch.float32, device=x.device) for _ in range(K)]
+        elif keep == "last" and K > 0 and agg != "last":
+            hops[K] = torch.empty((n, d), dtype=torch.float32, device=x.device)
+        out = None
+        if agg is not None:
+            out = torch.empty((n, (end - start) * d if agg == "concat" else d), dtype=torch.float32, device=x.device)
+        w = None
+        if weights is not None:
+            wl = [float(v) for v in weights]
+            if len(wl) != K + 1:
+                raise ValueError("propagate_fused: one weight per hop 0..K")
+            w = (c_float * (K + 1))(*wl)
+        ptrs = _lib.ptr_array([None] + [None if h is None else h.data_ptr() for h in hops[1:]])
+        ldx = int(x.stride(0)) if n > 1 else max(d, int(x.stride(0)))
+        if n and d:
+            with torch.cuda.device(self.device):
+                check(_lib.load().sglb200_propagate_fused(
+                    self._h, c_void_p(x.data_ptr()), ldx, ptrs, d, d, K, _MODES[mode], ops[agg], int(start), int(end), w,
+                    None if out is None else c_void_p(out.data_ptr()), 0 if out is None else int(out.shape[1]),
+                    int(bool(fuse_norm)), _stream_ptr()), "propagate_fused")
+        if agg == "last" and keep in ("last", "all"):
+            hops[K] = out
+        return hops, out
+
     # ---- K hops, host in / host out ---------------------------------------------------------------------------
     def propagate_host(self, x, prop_steps: int, mode="fast", keep: str = "all", pin: bool = True) -> List[torch.Tensor]:
         """Host [n,d] features in, K host tensors out (hop 1..K; keep='last' downloads only hop K).  Uploads, the

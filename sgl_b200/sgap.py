@@ -49,6 +49,21 @@ class BaseSGAPModel(nn.Module):
             self._processed_feature = feature
             return
         self._pre_msg_learnable = self._pre_msg_op.aggr_type in _LEARNABLE
+        spec = None
+        if self.fused_preprocess and not self._pre_msg_learnable and hasattr(self._pre_msg_op, "fused_spec") \
+                and hasattr(self._pre_graph_op, "propagate_aggregate_device") and feature.shape[1] <= 512:
+            spec = self._pre_msg_op.fused_spec(self._prop_steps)
+        if spec is not None:
+            # one pass per hop: normalisation, per-hop store (none needed) and the combiner run inside the hop kernel
+            _, out = self._pre_graph_op.propagate_aggregate_device(adj, feature, spec)
+            self._processed_feat_list = None
+            if self.feature_device == "cpu":
+                host = torch.empty(out.shape, dtype=out.dtype, pin_memory=True)
+                host.copy_(out, non_blocking=True)
+                torch.cuda.current_stream().synchronize()
+                out = host
+            self._processed_feature = out
+            return
         if self.fused_preprocess and hasattr(self._pre_graph_op, "propagate_device"):
             hops = self._pre_graph_op.propagate_device(adj, feature)
             self._processed_feat_list = hops                       # CUDA tensors

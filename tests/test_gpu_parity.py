@@ -119,7 +119,7 @@ def test_golden_combiners(message_golden):
 # --------------------------------------------------------------------------------------------------------------
 # oracle on seeded random inputs: every kernel shape, ragged rows, cut rows
 # --------------------------------------------------------------------------------------------------------------
-@pytest.mark.parametrize("d", [1, 3, 8, 16, 47, 64, 100, 128, 200, 256, 500, 1030])
+@pytest.mark.parametrize("d", [1, 3, 4, 8, 12, 16, 32, 47, 48, 64, 68, 100, 128, 200, 256, 500, 1030])
 def test_feature_widths_exact_and_fast(d):
     rng = np.random.default_rng(d)
     n = 700
@@ -154,6 +154,87 @@ def test_cut_rows_are_folded_deterministically(tile_items, split):
     assert np.array_equal(y1, y2)                           # run-to-run deterministic (no atomics)
     assert_close_1e5(y1, ref)
     assert np.array_equal(op.spmm(xd, mode="exact").cpu().numpy(), ref)
+    op.close()
+
+
+@pytest.mark.parametrize("d", [12, 16, 32, 64])
+def test_narrow_rows_lane_group_kernel_cut_rows_and_tile_ranges(d):
+    """d <= 64: several tiles per warp, one lane group each (spmm_group.cu) -- cut rows, tile ranges, accumulate."""
+    rng = np.random.default_rng(100 + d)
+    n = 900
+    adj = random_graph(rng, n, 40000, skew=1.2)
+    a = O.laplacian_adj(adj, 0.5)
+    x = rng.standard_normal((n, d)).astype(np.float32)
+    ref = O.spmm_hop(a, x, "fma")
+    op = CsrOperator(a.indptr, a.indices, a.data.astype(np.float32), a.shape, tile_items=64, split_threshold=24)
+    assert op.info()["carry_runs"] > 0
+    xd = torch.from_numpy(x).cuda()
+    y1 = op.spmm(xd, mode="fast")
+    assert torch.equal(y1, op.spmm(xd, mode="fast"))
+    assert_close_1e5(y1.cpu().numpy(), ref)
+    assert np.array_equal(op.spmm(xd, mode="exact").cpu().numpy(), ref)
+    tb, rb = op.chunks(3, mode="fast")
+    y3 = torch.full_like(y1, float("nan"))
+    for c in range(3):
+        op.spmm_tiles(xd, y3, tb[c], tb[c + 1], mode="fast")
+    assert torch.equal(y3, y1)
+    base = rng.standard_normal((n, d)).astype(np.float32)
+    yacc = torch.from_numpy(base).cuda()
+    op.spmm(xd, out=yacc, mode="exact", accumulate=True)
+    want = base.copy()
+    O._lib().oracle_spmm_f32_fma_i64(want, a.data.astype(np.float32), a.indices, a.indptr.astype(np.int64), x, n, d)
+    assert np.array_equal(yacc.cpu().numpy(), want)
+    op.close()
+
+
+@pytest.fixture()
+def tma_kernel(monkeypatch):
+    monkeypatch.setenv("SGLB200_TMA", "1")
+    yield
+
+
+@pytest.mark.parametrize("d", [68, 100, 128, 200, 256])
+@pytest.mark.parametrize("tile_items,split", [(0, 0), (64, 24), (32, 1)])
+def test_tma_staged_kernel_matches_oracle(tma_kernel, d, tile_items, split):
+    """spmm_tma.cu (gather4 feature rows + bulk-copied index stream): bit-exact in EXACT mode, 1e-5 in FAST mode with cut
+    rows, equal to the register-staged kernel's tile ranges, deterministic run to run."""
+    rng = np.random.default_rng(1000 + d + tile_items)
+    n = 1500
+    adj = random_graph(rng, n, 30000, skew=1.2, weights=True)
+    a = O.laplacian_adj(adj, 0.5)                      # full diagonal: no empty rows
+    x = rng.standard_normal((n, d)).astype(np.float32)
+    ref = O.spmm_hop(a, x, "fma")
+    op = CsrOperator(a.indptr, a.indices, a.data.astype(np.float32), a.shape, tile_items=tile_items, split_threshold=split)
+    xd = torch.from_numpy(x).cuda()
+    assert np.array_equal(op.spmm(xd, mode="exact").cpu().numpy(), ref)
+    y1 = op.spmm(xd, mode="fast")
+    assert torch.equal(y1, op.spmm(xd, mode="fast"))
+    assert_close_1e5(y1.cpu().numpy(), ref)
+    tb, rb = op.chunks(3, mode="fast")
+    y3 = torch.full_like(y1, float("nan"))
+    for c in range(3):
+        op.spmm_tiles(xd, y3, tb[c], tb[c + 1], mode="fast")
+    assert torch.equal(y3, y1)
+    # strided input and output (column blocks of a concat slab)
+    slab = torch.zeros((n, 3 * d), device="cuda")
+    slab[:, d:2 * d] = xd
+    op.spmm(slab[:, d:2 * d], out=slab[:, 2 * d:], mode="exact")
+    assert np.array_equal(slab[:, 2 * d:].cpu().numpy(), ref)
+    op.close()
+
+
+def test_tma_kernel_falls_back_on_graphs_with_empty_rows(tma_kernel):
+    rng = np.random.default_rng(77)
+    n, d = 500, 128
+    dense = (rng.random((n, n)) < 0.01).astype(np.float32)
+    dense[::7] = 0.0                                   # empty rows: the row-end flags cannot describe them
+    a = sp.csr_matrix(dense)
+    x = rng.standard_normal((n, d)).astype(np.float32)
+    op = CsrOperator(a.indptr, a.indices, a.data, a.shape)
+    y = op.spmm(torch.from_numpy(x).cuda(), mode="exact").cpu().numpy()
+    want = np.zeros((n, d), dtype=np.float32)
+    O._lib().oracle_spmm_f32_fma_i64(want, a.data, a.indices, a.indptr.astype(np.int64), x, n, d)
+    assert np.array_equal(y, want)
     op.close()
 
 
@@ -563,3 +644,114 @@ def test_label_propagation_and_nafs_features():
         want = O.nafs_smoothed_features(adj, x, 3, (0.5, 0.3, 0.0), method)
         assert got.shape == want.shape
         np.testing.assert_allclose(got, want, rtol=2e-5, atol=4e-6, err_msg=method)
+
+
+# --------------------------------------------------------------------------------------------------------------
+# g1: fused K-hop driver -- degree normalisation and cross-hop aggregation inside the hop kernel's row flush
+# --------------------------------------------------------------------------------------------------------------
+def _fused_reference(ref, agg, start, end, weights):
+    if agg == "sum":
+        return O.combine_sum(ref, start, end)
+    if agg == "mean":
+        return O.combine_mean(ref, start, end)
+    if agg == "max":
+        return O.combine_max(ref, start, end)
+    if agg == "min":
+        return O.combine_min(ref, start, end)
+    if agg == "concat":
+        return O.combine_concat(ref, start, end)
+    if agg == "weighted":
+        return O.combine_weighted(ref, np.asarray(weights[start:end], dtype=np.float32), start, end)
+    if agg == "last":
+        return ref[-1]
+    return O.combine_osd(ref)
+
+
+@pytest.mark.parametrize("d", [32, 100, 128])
+@pytest.mark.parametrize("use_tma", [False, True])
+def test_fused_driver_exact_mode_is_bit_exact(monkeypatch, d, use_tma):
+    """sglb200_propagate_fused, EXACT mode: hops and sum / mean / max / min / weighted / concat / last aggregates equal the
+    oracle's separate propagate + combine bit for bit (the running update keeps the reference's left-to-right order);
+    NAFS weights within 3e-6.  d=32: lane-group kernel, d=100/128: warp kernel or the TMA-staged kernel."""
+    if use_tma:
+        monkeypatch.setenv("SGLB200_TMA", "1")
+    rng = np.random.default_rng(500 + d)
+    n, K = 1200, 4
+    adj = random_graph(rng, n, 15000, skew=1.25, weights=True)
+    a = O.laplacian_adj(adj, 0.5)
+    x = rng.standard_normal((n, d)).astype(np.float32)
+    ref = O.propagate(a, x, K, "fma")
+    op = CsrOperator(a.indptr, a.indices, a.data.astype(np.float32), a.shape)
+    xd = torch.from_numpy(x).cuda()
+    wts = [0.5, 0.25, -0.125, 2.0, 0.3]
+    for agg, start, end in [("sum", 0, K + 1), ("mean", 1, K), ("max", 0, K + 1), ("min", 2, K + 1), ("weighted", 0, K + 1),
+                            ("weighted", 1, 4), ("concat", 0, K + 1), ("concat", 1, 3), ("last", 0, K + 1), ("osd", 0, K + 1)]:
+        hops, out = op.propagate_fused(xd, K, mode="exact", keep="none", agg=agg, start=start, end=end,
+                                       weights=wts if agg == "weighted" else None)
+        want = _fused_reference(ref, agg, start, end, wts)
+        if agg == "osd":
+            np.testing.assert_allclose(out.cpu().numpy(), want, rtol=3e-6, atol=3e-6)
+        else:
+            assert np.array_equal(out.cpu().numpy(), want), (agg, start, end)
+        assert all(h is None for h in hops[1:])
+    hops, out = op.propagate_fused(xd, K, mode="exact", keep="all", agg="mean")
+    for k in range(K + 1):
+        assert np.array_equal(hops[k].cpu().numpy(), ref[k])
+    assert np.array_equal(out.cpu().numpy(), O.combine_mean(ref, 0, K + 1))
+    hops, out = op.propagate_fused(xd, K, mode="exact", keep="last")
+    assert out is None and np.array_equal(hops[K].cpu().numpy(), ref[K]) and hops[1] is None
+    op.close()
+
+
+@pytest.mark.parametrize("kind,r,alpha", [("lap", 0.5, None), ("lap", 0.0, None), ("ppr", 0.5, 0.15)])
+@pytest.mark.parametrize("weighted", [False, True])
+@pytest.mark.parametrize("d", [16, 100, 128])
+def test_fused_normalisation_fast_mode(kind, r, alpha, weighted, d):
+    """FAST mode on a device-built operator: the hop streams raw weights (none when they are all 1) and applies
+    deg^(r-1), deg^(-r) and the PPR teleport term in the row flush.  Every hop within 1e-5 of the oracle (Frobenius and
+    max-abs relative), cut rows included; mean aggregate within 1e-5; equal to itself run to run."""
+    from sgl_b200.graph_build import operator_from_scipy_device
+    rng = np.random.default_rng(900 + d)
+    n, K = 2500, 4
+    rows = rng.integers(0, n, 30000)
+    cols = (rng.zipf(1.2, 30000) - 1) % n
+    if weighted:
+        adj = sp.csr_matrix((np.ones(60000, dtype=np.float32), (np.concatenate([rows, cols]), np.concatenate([cols, rows]))), shape=(n, n))
+    else:
+        adj = sp.csr_matrix((np.ones(60000, dtype=np.float32), (np.concatenate([rows, cols]), np.concatenate([cols, rows]))), shape=(n, n))
+        adj.data[:] = 1.0       # duplicates merged to weight 1: an unweighted graph
+    a = O.laplacian_adj(adj, r) if kind == "lap" else O.ppr_adj(adj, r, alpha)
+    x = rng.standard_normal((n, d)).astype(np.float32)
+    ref = O.propagate(a, x, K, "fma")
+    op = operator_from_scipy_device(adj, r=r, alpha=alpha, tile_items=64, split_threshold=24)
+    assert op.info()["carry_runs"] > 0
+    xd = torch.from_numpy(x).cuda()
+    hops, out = op.propagate_fused(xd, K, mode="fast", keep="all", agg="mean")
+    hops2, out2 = op.propagate_fused(xd, K, mode="fast", keep="all", agg="mean")
+    for k in range(1, K + 1):
+        assert_close_1e5(hops[k].cpu().numpy(), ref[k])
+        assert torch.equal(hops[k], hops2[k])
+    assert_close_1e5(out.cpu().numpy(), O.combine_mean(ref, 0, K + 1))
+    assert torch.equal(out, out2)
+    # without keeping the hops (internal ping-pong slabs only) the aggregate is the same bits
+    _, out3 = op.propagate_fused(xd, K, mode="fast", keep="none", agg="mean")
+    assert torch.equal(out, out3)
+    # fuse_norm=False streams the materialised float32 values: same tolerance, and EXACT stays bit-exact
+    hops4, _ = op.propagate_fused(xd, K, mode="fast", keep="all", fuse_norm=False)
+    assert_close_1e5(hops4[K].cpu().numpy(), ref[K])
+    hops5, _ = op.propagate_fused(xd, K, mode="exact", keep="all")
+    assert np.array_equal(hops5[K].cpu().numpy(), ref[K])
+    op.close()
+
+
+def test_message_ops_keep_the_autograd_graph():
+    """combiners fed with tensors that require grad must stay differentiable (reference _combine is torch)."""
+    feats = [torch.randn(50, 8, device="cuda", requires_grad=True) for _ in range(4)]
+    for op in (SumMessageOp(0, 4), MeanMessageOp(1, 3), MaxMessageOp(0, 4), MinMessageOp(0, 4), ConcatMessageOp(0, 3),
+               SimpleWeightedMessageOp(0, 4, "alpha", 0.85), OverSmoothDistanceWeightedOp()):
+        out = op.aggregate(feats)
+        assert out.requires_grad, type(op).__name__
+        out.sum().backward()
+    assert all(f.grad is not None for f in feats)
+    with torch.no_grad():
+        assert not SumMessageOp(0, 4).aggregate(feats).requires_grad
