@@ -1,17 +1,23 @@
 #!/usr/bin/env python
 """bench.py -- K-hop CSR-SpMM propagation throughput on B200 (BASELINE.json metric).
 
-    python bench.py [--gpus N] [--steps K] [--warmup W] [--workload arxiv|products|pubmed|rmatS] [--impl reference]
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--workload products|arxiv|pubmed|rmatS] [--impl reference]
 
 One "step" = one full pass of the hot path over the workload: the K hops  X -> A^X -> ... -> A^^K X  of the
-normalised adjacency (GraphOp.propagate minus the one-time normalisation, which is reported separately).
+normalised adjacency (GraphOp.propagate minus the one-time normalisation, which is reported under "setup").
+Default workload at every N: products-shape (BASELINE configs[2]: N=2,449,029, nnz(A^) ~ 121 M, d=100, K=6), the
+largest single-GPU configuration of BASELINE.json; the same graph at N = 1, 2, 4, 8 => strong scaling.
 Prints ONE JSON line (contract in the task statement):
-  value     whole-job propagated edges/s = nnz(A^) * K * steps / device time, inputs resident in HBM
-  e2e       same metric through CsrOperator.propagate_host (C ABI sglb200_propagate_host): pinned host X in,
-            K pinned host slabs out, H2D/D2H inside the timed region
-  roofline  achieved algorithmic GB/s of the hop kernel vs the measured HBM peak (MEASURED_PEAKS.json)
+  value     whole-job propagated edges/s = nnz(A^) * K * steps / device time (max over ranks), inputs resident in HBM
+  e2e       same metric through the reference-facing API with HOST buffers: GraphOp.propagate of a stand-in of the
+            reference's own class re-routed by sgl_b200.patch.install() (pinned host X in, K+1 host tensors out)
+  roofline  achieved algorithmic GB/s of the hop kernel vs the measured HBM peak, with the DRAM traffic of one launch
+            measured in this run by an ncu child process
   cpu_baseline  the reference's own CPU kernel (oracle/_ref, compiled from its matmul.c) on this box's host cores
-`--impl reference` times that CPU kernel as the step and prints the same line with "impl": "reference".
+N > 1: one process per GPU (torchrun).  Default partition "feature": A^ replicated (it fits in 180 GB for every
+BASELINE config), the feature columns split across the GPUs, no per-hop exchange, one all-to-all of the last hop into
+row shards.  `--partition row` runs the 1-D row partition with the halo exchange per hop (sgl_b200.dist).
+`--impl reference` times the reference CPU kernel as the step and prints the same line with "impl": "reference".
 """
 from __future__ import annotations
 
@@ -20,6 +26,7 @@ import json
 import os
 import subprocess
 import sys
+import tempfile
 import threading
 import time
 
@@ -34,11 +41,12 @@ UNIT = "edges/s"
 
 # shape-matched synthetics of BASELINE.json's configs; the datasets are not available offline
 WORKLOADS = {
-    #            N          directed edges   R-MAT scale  d    K   undirected?
+    #            N          directed edges   R-MAT scale  d    K
     "pubmed":   (19_717,    44_324,          15,          500, 3),
     "arxiv":    (169_343,   1_166_243,       18,          128, 5),
     "products": (2_449_029, 61_859_140,      22,          100, 6),
 }
+CONFIG_INDEX = {"pubmed": 0, "arxiv": 1, "products": 2}
 
 
 def parse_args():
@@ -51,20 +59,24 @@ def parse_args():
     ap.add_argument("--mode", default="fast", choices=["fast", "exact"])
     ap.add_argument("--tile-items", type=int, default=0)
     ap.add_argument("--split-threshold", type=int, default=0)
-    ap.add_argument("--no-cpu-baseline", action="store_true")
-    ap.add_argument("--no-e2e", action="store_true")
-    ap.add_argument("--exchange", default="halo", choices=["halo", "allgather"])
-    ap.add_argument("--transport", default="peer", choices=["peer", "nccl"],
-                    help="halo rows move by our NVLink peer-store kernels (CUDA IPC) or by NCCL all_to_all")
-    ap.add_argument("--partition", default="row", choices=["row", "feature"],
-                    help="N>1: 1-D row partition with a halo exchange per hop (default, SURVEY 8e), or A^ replicated and the "
-                         "feature columns split across GPUs (no per-hop exchange; one all-gather of the last hop)")
-    ap.add_argument("--plan", default="replicated", choices=["replicated", "collective"],
-                    help="halo plan from the full matrix on every rank (numpy) or built collectively from local rows (torch)")
     ap.add_argument("--feat-dim", type=int, default=0, help="experiment: override the feature width of the workload")
     ap.add_argument("--relabel", default="none", choices=["none", "degree"],
                     help="experiment: relabel the vertices by descending degree before building A^")
-    ap.add_argument("--chunks", type=int, default=4, help="row chunks the hop is pipelined over against its halo exchange")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--no-comparators", action="store_true")
+    ap.add_argument("--traffic", default="ncu", choices=["ncu", "file", "none"],
+                    help="roofline.traffic: measured by an ncu child process in this run (default), read from "
+                         "profiles/traffic.json, or omitted")
+    ap.add_argument("--traffic-child", action="store_true", help=argparse.SUPPRESS)
+    ap.add_argument("--partition", default="feature", choices=["feature", "row"],
+                    help="N>1: A^ replicated and the feature columns split (default; no per-hop exchange), or the 1-D row "
+                         "partition with a halo exchange per hop (SURVEY 8e)")
+    ap.add_argument("--exchange", default="halo", choices=["halo", "allgather"])
+    ap.add_argument("--transport", default="peer", choices=["peer", "nccl"],
+                    help="row partition: halo rows move by our NVLink peer-store kernels (CUDA IPC) or by NCCL all_to_all")
+    ap.add_argument("--plan", default="replicated", choices=["replicated", "collective"])
+    ap.add_argument("--chunks", type=int, default=4, help="row partition: chunks the hop is pipelined over")
     return ap.parse_args()
 
 
@@ -90,20 +102,28 @@ def rmat_edges(n, m, scale, seed, device):
     return src, dst
 
 
+def workload_shape(name):
+    if name.startswith("rmat"):
+        scale = int(name[4:])
+        return 1 << scale, 8 << scale, scale, 128, 10
+    return WORKLOADS[name]
+
+
+def device_graph(name, dev):
+    """Edges of the workload on the device: (rows, cols, n, d, K) with the symmetrisation the reference applies."""
+    import torch
+    n, m, scale, d, K = workload_shape(name)
+    seed = {"pubmed": 0, "arxiv": 1, "products": 2}.get(name, 4)
+    src, dst = rmat_edges(n, m, scale, seed, dev)
+    return torch.cat([src, dst]), torch.cat([dst, src]), n, d, K
+
+
 def build_adjacency(name, device):
     """scipy CSR (float32, int32) of the symmetrised graph: concatenation without dedup, duplicates summed
     (reference sgl/data/utils.py:18-24 + sgl/data/base_data.py:29-30)."""
     import scipy.sparse as sp
     import torch
-    if name.startswith("rmat"):
-        scale = int(name[4:])
-        n, m, d, K = 1 << scale, 8 << scale, 128, 10
-    else:
-        n, m, scale, d, K = WORKLOADS[name]
-    seed = {"pubmed": 0, "arxiv": 1, "products": 2}.get(name, 4)
-    src, dst = rmat_edges(n, m, scale, seed, device)
-    rows = torch.cat([src, dst])
-    cols = torch.cat([dst, src])
+    rows, cols, n, d, K = device_graph(name, device)
     keys, counts = torch.unique(rows * n + cols, return_counts=True)   # sorted (row, col), multiplicities
     rows = torch.div(keys, n, rounding_mode="floor")
     cols = keys - rows * n
@@ -117,6 +137,26 @@ def build_adjacency(name, device):
 def algorithmic_bytes_per_hop(n, nnz, d):
     """fp32 values + int32 column ids + int64 row pointers, X read once, Y written once."""
     return 8 * nnz + 8 * (n + 1) + 8 * n * d
+
+
+def algorithmic_bytes_per_hop_fused(n, nnz, d):
+    """fused normalisation, unit weights: 4 B/edge, row pointers, two degree vectors, X and Y once."""
+    return 4 * nnz + 8 * (n + 1) + 8 * n + 8 * n * d
+
+
+def workload_config(name, n, nnz, d, K, args):
+    idx = CONFIG_INDEX.get(name, 4)
+    return {"workload": f"{name}-shape synthetic R-MAT (BASELINE configs[{idx}])", "N": n, "nnz": nnz, "d": d,
+            "prop_steps": K, "operator": "LaplacianGraphOp r=0.5", "mode": args.mode,
+            "l2": "256 MiB buffer written between timed steps (L2 flush); K+1 slabs + CSR exceed L2"}
+
+
+def hbm_peak():
+    try:
+        peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+        return float(peaks["hbm_gbs"]), "MEASURED_PEAKS.json hbm_gbs (measured copy bandwidth)"
+    except Exception:
+        return 6650.0, "fallback 6650 GB/s (B200_PROFILING.md)"
 
 
 # ---------------------------------------------------------------------------------------------------------------
@@ -203,52 +243,147 @@ def cpu_reference_steps(adj_norm, x, K, steps, warmup, budget_s=None):
     return times, kind, O.num_threads()
 
 
+def host_normalised_adjacency(name, dev):
+    """float64 scipy CSR of A^ for the host arms: built on the GPU when there is one (same bits, tests/test_gpu_parity.py),
+    else with the host recipe."""
+    import torch
+    if torch.cuda.is_available():
+        from sgl_b200.graph_build import normalized_adjacency_device, parts_to_scipy
+        rows, cols, n, d, K = device_graph(name, dev)
+        parts = normalized_adjacency_device(rows, cols, n, None, r=0.5, alpha=None, pow_on="host")
+        adj_norm = parts_to_scipy(parts)
+        del parts, rows, cols
+        torch.cuda.empty_cache()
+        return adj_norm, d, K
+    from sgl_b200.operators.utils import adj_to_symmetric_norm
+    adj, d, K = build_adjacency(name, dev)
+    return adj_to_symmetric_norm(adj, 0.5).tocsr(), d, K
+
+
 def run_reference(args):
     import torch
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
-    name = args.workload or "arxiv"
-    adj, d, K = build_adjacency(name, "cuda" if torch.cuda.is_available() else "cpu")
-    from sgl_b200.operators.utils import adj_to_symmetric_norm
-    adj_norm = adj_to_symmetric_norm(adj, 0.5).tocsr()
-    n, nnz = adj.shape[0], adj_norm.nnz
+    name = args.workload or "products"
+    dev = torch.device("cuda", 0) if torch.cuda.is_available() else torch.device("cpu")
+    adj_norm, d, K = host_normalised_adjacency(name, dev)
+    n, nnz = adj_norm.shape[0], adj_norm.nnz
     x = torch.randn(n, d, generator=torch.Generator().manual_seed(0)).numpy()
-    times, kind, threads = cpu_reference_steps(adj_norm, x, K, args.steps, args.warmup, budget_s=240.0)
+    # bounded: at most `steps` full passes, stop after ~100 s of CPU work (one products-shape pass is ~10 s on 64 threads)
+    times, kind, threads = cpu_reference_steps(adj_norm, x, K, args.steps, min(args.warmup, 1), budget_s=100.0)
     sec = float(np.sum(times))
     value = nnz * K * len(times) / sec
     line = {"impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus,
-            "steps": len(times), "warmup": args.warmup, "ms_per_step": 1e3 * sec / len(times),
+            "steps": len(times), "warmup": min(args.warmup, 1), "ms_per_step": 1e3 * sec / len(times),
             "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
             "config": workload_config(name, n, nnz, d, K, args),
             "cpu_baseline": {"value": value, "unit": UNIT, "cores": threads, "kind": kind,
-                             "sample": f"full workload, {len(times)} steps of K={K} hops, bare kernel (no wrapper copies)"},
+                             "sample": f"{len(times)} full passes of K={K} hops over the whole graph (bounded to ~100 s), "
+                                       "bare kernel (no wrapper copies)"},
             "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
     print(json.dumps(line))
 
 
-def workload_config(name, n, nnz, d, K, args):
-    return {"workload": f"{name}-shape synthetic R-MAT (BASELINE configs[{ {'pubmed': 0, 'arxiv': 1, 'products': 2}.get(name, 4)}])",
-            "N": n, "nnz": nnz, "d": d, "prop_steps": K, "operator": "LaplacianGraphOp r=0.5",
-            "mode": args.mode, "partition": "single GPU" if args.gpus == 1 else f"1-D row partition x{args.gpus}",
-            "l2": "256 MiB buffer written between timed steps (L2 flush); K+1 slabs + CSR exceed L2"}
+# ---------------------------------------------------------------------------------------------------------------
+# roofline.traffic: DRAM bytes of one hop launch, measured by an ncu child of this very command
+# ---------------------------------------------------------------------------------------------------------------
+def measure_traffic(args, name, K):
+    """dram__bytes_read.sum + dram__bytes_write.sum of ONE hop launch (the second hop of a step after warm-up)."""
+    if args.traffic == "none":
+        return None, "not measured"
+    if args.traffic == "file":
+        return traffic_from_file(name)
+    skip = 3 * K + 1
+    cmd = ["ncu", "--metrics", "dram__bytes_read.sum,dram__bytes_write.sum", "--clock-control", "none", "-k",
+           "regex:spmm_(flat|group|tma)_kernel", "-s", str(skip), "-c", "1", "--csv", sys.executable,
+           os.path.abspath(__file__), "--traffic-child", "--workload", name, "--mode", args.mode]
+    if args.feat_dim:
+        cmd += ["--feat-dim", str(args.feat_dim)]
+    try:
+        out = subprocess.run(cmd, capture_output=True, text=True, timeout=240).stdout
+        total = 0.0
+        found = 0
+        for ln in out.splitlines():
+            if "dram__bytes_" in ln and ".sum" in ln:
+                cells = [c.strip('"') for c in ln.split('","')]
+                unit, val = cells[-2].lower(), float(cells[-1].replace(",", ""))
+                total += val * {"byte": 1.0, "kbyte": 1e3, "mbyte": 1e6, "gbyte": 1e9}.get(unit, 1.0)
+                found += 1
+        if found >= 2 and total > 0:
+            return total, "ncu child process in this run (dram__bytes_read.sum + dram__bytes_write.sum of one hop launch)"
+    except Exception:
+        pass
+    val, src = traffic_from_file(name)
+    return val, src + " (ncu child unavailable)"
+
+
+def traffic_from_file(name):
+    try:
+        t = json.load(open(os.path.join(ROOT, "profiles", "traffic.json")))
+        ent = t.get("workloads", {}).get(name)
+        if ent:
+            return float(ent["dram_bytes_per_launch"]), "profiles/traffic.json (" + ent.get("source", "ncu") + ")"
+    except Exception:
+        pass
+    return None, "not measured"
+
+
+def run_traffic_child(args):
+    """What the ncu child runs: the same operator, 3 warm-up steps and one more step of plain hops."""
+    import torch
+    from sgl_b200.graph_build import build_operator_device
+    dev = torch.device("cuda", 0)
+    torch.cuda.set_device(0)
+    name = args.workload or "products"
+    rows, cols, n, d, K = device_graph(name, dev)
+    if args.feat_dim > 0:
+        d = args.feat_dim
+    op = build_operator_device(rows, cols, n, r=0.5)
+    del rows, cols
+    hops = [torch.randn(n, d, device=dev)] + [torch.empty(n, d, device=dev) for _ in range(K)]
+    for _ in range(4):
+        for k in range(1, K + 1):
+            op.spmm(hops[k - 1], out=hops[k], mode=args.mode)
+    torch.cuda.synchronize()
 
 
 # ---------------------------------------------------------------------------------------------------------------
-# B200 arm
+# B200 arm, one GPU
 # ---------------------------------------------------------------------------------------------------------------
+def oracle_rows(sub, x_host, d):
+    from oracle import sgap_oracle as O
+    ref = np.zeros((sub.shape[0], d), dtype=np.float32)
+    O._lib().oracle_spmm_f32_fma_i64(ref, sub.data, sub.indices.astype(np.int32), sub.indptr.astype(np.int64),
+                                     np.ascontiguousarray(x_host), sub.shape[0], d)
+    return ref
+
+
+def standin_reference_classes():
+    """A stand-in of the reference's `sgl.operators` package (tests/standin/make_standin.py: same module paths, names and
+    ctypes binding as the reference; the GPU box has no /root/reference), re-routed by sgl_b200.patch.install()."""
+    sys.path.insert(0, os.path.join(ROOT, "tests", "standin"))
+    import make_standin
+    root = make_standin.write(tempfile.mkdtemp(prefix="sgl_standin_"))
+    sys.path.insert(0, root)
+    import importlib
+    graph_op = importlib.import_module("sgl.operators.graph_op")
+    import sgl_b200.patch as patch
+    patch.install()
+    return graph_op, patch
+
+
 def run_b200(args):
     import torch
-    from sgl_b200.operators.graph_op import LaplacianGraphOp
-    from sgl_b200.runtime import CsrOperator
-
+    if args.traffic_child:
+        return run_traffic_child(args)
     if args.gpus > 1 or int(os.environ.get("WORLD_SIZE", "1")) > 1:
-        return run_dist(args)
+        return run_feature_split(args) if args.partition == "feature" else run_row_partition(args)
+    from sgl_b200.graph_build import build_operator_device, parts_to_scipy
 
     torch.cuda.set_device(0)
     dev = torch.device("cuda", 0)
-    name = args.workload or "arxiv"
-    from sgl_b200.graph_build import build_operator_device, parts_to_scipy
+    name = args.workload or "products"
     t0 = time.perf_counter()
     rows, cols, n, d, K = device_graph(name, dev)
     if args.feat_dim > 0:
@@ -263,22 +398,15 @@ def run_b200(args):
     torch.cuda.synchronize()
     t_gen = time.perf_counter() - t0
     # A^ = D^-1/2 (A+I)^T D^-1/2 built on the device (sgl_b200.graph_build: bit-identical structure and values to the
-    # reference's scipy pass, tests/test_gpu_parity.py); the reference's own host pass is timed for small graphs only
+    # reference's scipy pass, tests/test_gpu_parity.py)
     t0 = time.perf_counter()
     op = build_operator_device(rows, cols, n, r=0.5, tile_items=args.tile_items, split_threshold=args.split_threshold)
     torch.cuda.synchronize()
-    t_upload = time.perf_counter() - t0
+    t_build = time.perf_counter() - t0
     del rows, cols
     adj_norm = parts_to_scipy(op.parts)
     op.parts = None
     torch.cuda.empty_cache()
-    t_norm = None
-    if n <= 500_000:
-        adj, _, _ = build_adjacency(name, dev)
-        t0 = time.perf_counter()
-        host_norm = LaplacianGraphOp(K, r=0.5)._construct_adj(adj)
-        t_norm = time.perf_counter() - t0
-        assert np.array_equal(host_norm.indices, adj_norm.indices) and np.array_equal(host_norm.data, adj_norm.data)
     nnz = int(adj_norm.nnz)
     info = op.info()
 
@@ -315,50 +443,169 @@ def run_b200(args):
     value = nnz * K * args.steps / total_s
     hop_s = total_s / (args.steps * K)
 
-    peaks = {}
-    peak_src = "fallback 6650 GB/s (B200_PROFILING.md)"
-    try:
-        peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
-        peak_gbs, peak_src = float(peaks["hbm_gbs"]), "MEASURED_PEAKS.json hbm_gbs (measured copy bandwidth)"
-    except Exception:
-        peak_gbs = 6650.0
+    # ---- the fused driver on the same workload: in-kernel normalisation + mean aggregation, no hop stored -----------
+    fused = None
+    if d <= 512:
+        for _ in range(2):
+            op.propagate_fused(hops[0], K, mode=args.mode, keep="none", agg="mean")
+        torch.cuda.synchronize()
+        f_steps = max(3, min(args.steps, 10))
+        ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        ms = 0.0
+        for i in range(f_steps):
+            flush.fill_(i & 0xFF)
+            ev0.record(stream)
+            op.propagate_fused(hops[0], K, mode=args.mode, keep="none", agg="mean")
+            ev1.record(stream)
+            torch.cuda.synchronize()
+            ms += ev0.elapsed_time(ev1)
+        fused = {"value": nnz * K * f_steps / (ms / 1e3), "unit": UNIT, "ms_per_step": ms / f_steps,
+                 "what": "sglb200_propagate_fused: K hops + degree normalisation + MeanMessageOp in the hop kernel's row flush "
+                         "(SSGC preprocess), no per-hop slab stored, no aggregation pass",
+                 "algorithmic_bytes_per_hop_fused": algorithmic_bytes_per_hop_fused(n, nnz, d) + 8 * n * d}
+
+    peak_gbs, peak_src = hbm_peak()
     b_alg = algorithmic_bytes_per_hop(n, nnz, d)
     achieved = b_alg / hop_s / 1e9
+    traffic, traffic_src = measure_traffic(args, name, K)
+    kernel = "spmm_group_kernel" if (d % 4 == 0 and d <= 64) else "spmm_flat_kernel"
     roofline = {"bound": "hbm", "achieved": achieved, "peak": peak_gbs, "unit": "GB/s", "frac": achieved / peak_gbs,
-                "traffic": None, "kernel": "spmm_flat_kernel<4,1,8>", "algorithmic_bytes_per_launch": b_alg,
+                "traffic": traffic, "traffic_source": traffic_src, "kernel": kernel,
+                "algorithmic_bytes_per_launch": b_alg,
+                "algorithmic_bytes_per_launch_fused": algorithmic_bytes_per_hop_fused(n, nnz, d),
                 "gather_bytes_per_launch": nnz * (8 + 4 * d) + n * (8 + 4 * d), "us_per_launch": hop_s * 1e6,
+                "dram_measured_frac": (traffic / hop_s / 1e9 / peak_gbs) if traffic else None,
                 "peak_source": peak_src}
-    prof = os.path.join(ROOT, "profiles", "traffic.json")
-    if os.path.exists(prof):
-        try:
-            t = json.load(open(prof))
-            if t.get("workload") == name:
-                roofline["traffic"] = t.get("dram_bytes_per_launch")
-        except Exception:
-            pass
 
     # ---- parity spot check on the timed buffers: every hop against the oracle on a row sample -------------------
-    from oracle import sgap_oracle as O
     rng = np.random.default_rng(1)
     sample = np.sort(rng.choice(n, min(n, 2000), replace=False))
     sub = adj_norm[sample].astype(np.float32)
+    sample_t = torch.from_numpy(sample).to(dev)
     worst = 0.0
     for k in range(1, K + 1):
-        ref = np.zeros((sample.size, d), dtype=np.float32)
-        O._lib().oracle_spmm_f32_fma_i64(ref, sub.data, sub.indices.astype(np.int32), sub.indptr.astype(np.int64),
-                                         hops[k - 1].cpu().numpy(), sample.size, d)
-        got = hops[k][torch.from_numpy(sample).to(dev)].cpu().numpy()
+        ref = oracle_rows(sub, hops[k - 1].cpu().numpy(), d)
+        got = hops[k][sample_t].cpu().numpy()
         worst = max(worst, float(np.abs(got - ref).max() / max(np.abs(ref).max(), 1e-30)))
     assert worst <= 1e-5, f"bench parity check failed: {worst}"
+    last_hop_sample = hops[K][sample_t].cpu().numpy()
 
-    # ---- end to end through the public API with host buffers ------------------------------------------------------
-    # the call a user makes: SGC(prop_steps=K).preprocess(adj, x) -- configs[1] is SGC, whose LastMessageOp consumes
-    # only hop K.  Inside the timed region: H2D of x from pinned host memory, K hops, aggregate, D2H of the result into
-    # pinned host memory.  A^ is prepared once (GraphOp.prepare: the one-time setup reported under "setup").
+    # ---- end to end through the reference-facing API with host buffers ----------------------------------------------
     e2e = None
     if not args.no_e2e and n <= 8_000_000:
+        e2e = end_to_end(args, name, op, x_host, n, nnz, d, K, dev, sample, last_hop_sample)
+
+    # ---- GPU comparator: cuSPARSE SpMM (the reference's own dormant GPU choice, csrc/cudamatmul.c:104-119) -----------
+    comparators = {}
+    if not args.no_comparators:
+        try:
+            a_t = torch.sparse_csr_tensor(torch.from_numpy(adj_norm.indptr.astype(np.int64)).to(dev),
+                                          torch.from_numpy(adj_norm.indices.astype(np.int64)).to(dev),
+                                          torch.from_numpy(adj_norm.data.astype(np.float32)).to(dev), size=(n, n))
+            cur = hops[0]
+            for _ in range(2):
+                cur = torch.sparse.mm(a_t, hops[0])
+            torch.cuda.synchronize()
+            c_steps = max(2, min(args.steps, 5))
+            ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            ms = 0.0
+            for i in range(c_steps):
+                flush.fill_(i & 0xFF)
+                ev0.record(stream)
+                cur = hops[0]
+                for _ in range(K):
+                    cur = torch.sparse.mm(a_t, cur)
+                ev1.record(stream)
+                torch.cuda.synchronize()
+                ms += ev0.elapsed_time(ev1)
+            err = float((cur - hops[K]).abs().max() / hops[K].abs().max())
+            comparators["cusparse_spmm_via_torch"] = {"value": nnz * K * c_steps / (ms / 1e3), "unit": UNIT,
+                                                       "us_per_hop": 1e3 * ms / (c_steps * K), "max_rel_diff_vs_ours": err,
+                                                       "note": "torch.sparse.mm on a CSR tensor (cuSPARSE SpMM), device resident, "
+                                                               "same graph and features; a library call, reported for context"}
+            del a_t, cur
+        except Exception as exc:  # the comparator must never break the bench line
+            comparators["cusparse_spmm_via_torch"] = {"unavailable": str(exc)[:200]}
+
+    cpu = None
+    if not args.no_cpu_baseline:
+        # bounded sample: 1-2 full passes (~10 s each at products-shape)
+        times, kind, threads = cpu_reference_steps(adj_norm, x_host.numpy(), K, steps=2, warmup=0, budget_s=15.0)
+        cpu = {"value": nnz * K * len(times) / float(np.sum(times)), "unit": UNIT, "cores": threads, "kind": kind,
+               "sample": f"{len(times)} full pass(es) of K={K} hops over the whole graph (bounded to ~15-30 s), bare kernel"}
+
+    # cut rows are folded inside the hop kernel (one launch per hop) unless the separate fold launch is selected
+    separate_fold = os.environ.get("SGLB200_FOLD", "kernel").startswith("f") or d > 512
+    launches_per_step = K * (1 + (1 if info["carry_runs"] > 0 and args.mode == "fast" and separate_fold else 0))
+    line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": 1, "steps": args.steps, "warmup": max(args.warmup, 3),
+            "ms_per_step": 1e3 * total_s / args.steps, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
+            "dtype": "f32", "data": "synthetic", "config": workload_config(name, n, nnz, d, K, args),
+            "partition": "single GPU", "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e, "fused": fused,
+            "comparators": comparators, "clocks": clocks, "gpu_launches": launches_per_step * args.steps,
+            "parity": {"checked": "every hop vs oracle fma chain on 2000 sampled rows", "max_rel_err": worst},
+            "setup": {"generate_s": t_gen, "build_on_device_s": t_build, "tiles": info["tiles_fast"],
+                      "cut_rows": info["carry_runs"], "tile_items": info["tile_items"],
+                      "split_threshold": info["split_threshold"], "bytes_resident": info["bytes_resident"]}}
+    print(json.dumps(line))
+
+
+def end_to_end(args, name, op, x_host, n, nnz, d, K, dev, sample, last_hop_sample):
+    """The call a user of the reference makes, with host buffers, H2D/D2H inside the timed region.
+    value: LaplacianGraphOp(K).propagate(adj, x) on the stand-in of the reference's class after patch.install() -- pinned
+    host x in, K+1 host tensors out (what GAMLP.preprocess keeps, models/base_model.py:27-29); A^ is normalised by the
+    class' own scipy `_construct_adj` and uploaded on the FIRST call (reported as one-time setup), later calls on the same
+    adjacency reuse the resident operator (sgl_b200.operators.base_op.adjacency_fingerprint).
+    sub-keys: the SGC leg (fused preprocess, only the aggregate crosses PCIe) and the bare C-ABI propagate_host."""
+    import torch
+    adj, _, _ = build_adjacency(name, dev)
+    x_np = x_host.numpy()                      # numpy view of the pinned buffer: what the reference API takes
+    e2e_steps = max(3, min(args.steps, 5))
+    out = {"unit": UNIT, "h2d_bytes_per_step": n * d * 4, "d2h_bytes_per_step": K * n * d * 4, "steps": e2e_steps}
+    try:
+        graph_op, patch = standin_reference_classes()
+        ref_op = graph_op.LaplacianGraphOp(K, r=0.5)
+        ref_op.mode = args.mode
+        t0 = time.perf_counter()
+        res = ref_op.propagate(adj, x_np)      # first call: scipy normalisation + upload + hops + download
+        t_first = time.perf_counter() - t0
+        del res
+        res = ref_op.propagate(adj, x_np)      # pinned result buffers now come from torch's host allocator cache
+        del res
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        for _ in range(e2e_steps):
+            res = ref_op.propagate(adj, x_np)
+            got = res[K].numpy()[sample]
+            del res
+        dt = time.perf_counter() - t0
+        assert float(np.abs(got - last_hop_sample).max()) == 0.0
+        out.update({"value": nnz * K * e2e_steps / dt, "ms_per_step": 1e3 * dt / e2e_steps, "first_call_s": t_first,
+                    "api": "stand-in of sgl.operators.graph_op.LaplacianGraphOp + sgl_b200.patch.install(): propagate(adj, x) "
+                           "-> K+1 host tensors; A^ normalised (scipy, the class' own _construct_adj) and uploaded on the first "
+                           "call, reused afterwards"})
+        patch.uninstall()
+        ref_op._operator.close()
+    except Exception as exc:
+        out.update({"value": None, "error": str(exc)[:300]})
+    # C ABI entry point with host pointers: all K hops to the host
+    for _ in range(2):
+        op.propagate_host(x_host, K, mode=args.mode, keep="all")
+    t0 = time.perf_counter()
+    for _ in range(e2e_steps):
+        outs = op.propagate_host(x_host, K, mode=args.mode, keep="all")
+        last = outs[-1].numpy()[sample]
+        del outs
+    dt = time.perf_counter() - t0
+    assert float(np.abs(last - last_hop_sample).max()) == 0.0
+    out["all_hops_to_host"] = {"value": nnz * K * e2e_steps / dt, "ms_per_step": 1e3 * dt / e2e_steps,
+                               "d2h_bytes_per_step": K * n * d * 4,
+                               "api": "CsrOperator.propagate_host -> sglb200_propagate_host (K pinned slabs out)"}
+    if out.get("value") is None:
+        out["value"] = out["all_hops_to_host"]["value"]
+        out["ms_per_step"] = out["all_hops_to_host"]["ms_per_step"]
+    # SGC leg: fused preprocess through our model glue (LastMessageOp consumes only hop K)
+    try:
         from sgl_b200.sgap import SGC
-        adj, _, _ = build_adjacency(name, dev)
         model = SGC(prop_steps=K, feat_dim=d, output_dim=8)
         model._pre_graph_op.mode = args.mode
         model._pre_graph_op.build_on = "device"
@@ -366,8 +613,7 @@ def run_b200(args):
         model._pre_graph_op.prepare(adj)
         torch.cuda.synchronize()
         t_prepare = time.perf_counter() - t0
-        e2e_steps = max(3, min(args.steps, 20))
-        for _ in range(3):
+        for _ in range(2):
             model.preprocess(adj, x_host)
         torch.cuda.synchronize()
         t0 = time.perf_counter()
@@ -377,108 +623,210 @@ def run_b200(args):
         torch.cuda.synchronize()
         dt = time.perf_counter() - t0
         assert not result.is_cuda and result.shape == (n, d)
-        e2e = {"value": nnz * K * e2e_steps / dt, "unit": UNIT, "h2d_bytes_per_step": n * d * 4,
-               "d2h_bytes_per_step": n * d * 4, "ms_per_step": 1e3 * dt / e2e_steps, "steps": e2e_steps,
-               "prepare_graph_once_s": t_prepare,
-               "api": "sgl_b200.sgap.SGC.preprocess(adj, x): pinned host x in -> K hops + LastMessageOp on the GPU -> "
-                      "pinned host [N,d] out; A^ prepared once with GraphOp.prepare(adj)"}
-        # all K hops to the host (what GraphOp.propagate returns in the reference), through the C ABI entry point
-        for _ in range(2):
-            op.propagate_host(x_host, K, mode=args.mode, keep="all")
-        t0 = time.perf_counter()
-        for _ in range(max(3, e2e_steps // 2)):
-            outs = op.propagate_host(x_host, K, mode=args.mode, keep="all")
-        dt = time.perf_counter() - t0
-        e2e["all_hops_to_host"] = {"value": nnz * K * max(3, e2e_steps // 2) / dt, "d2h_bytes_per_step": K * n * d * 4,
-                                   "api": "CsrOperator.propagate_host -> sglb200_propagate_host (K pinned slabs out)"}
-        got = result.numpy()[sample]
-        assert float(np.abs(got - hops[K][torch.from_numpy(sample).to(dev)].cpu().numpy()).max()) == 0.0
-        assert float(np.abs(outs[-1].numpy()[sample] - got).max()) == 0.0
+        err = float(np.abs(result.numpy()[sample] - last_hop_sample).max() / max(np.abs(last_hop_sample).max(), 1e-30))
+        assert err <= 1e-5, err
+        out["sgc_preprocess"] = {"value": nnz * K * e2e_steps / dt, "ms_per_step": 1e3 * dt / e2e_steps,
+                                 "h2d_bytes_per_step": n * d * 4, "d2h_bytes_per_step": n * d * 4,
+                                 "prepare_graph_once_s": t_prepare, "max_rel_diff_vs_plain_hops": err,
+                                 "api": "sgl_b200.sgap.SGC.preprocess(adj, x): pinned host x in -> fused K hops (in-kernel "
+                                        "normalisation, LastMessageOp) -> pinned host [N,d] out; A^ built on the device once"}
         model._pre_graph_op._operator.close()
-
-    # ---- GPU comparator: cuSPARSE SpMM (the reference's own dormant GPU choice, csrc/cudamatmul.c:104-119) -------------
-    comparators = {}
-    try:
-        a_t = torch.sparse_csr_tensor(torch.from_numpy(adj_norm.indptr.astype(np.int64)).to(dev),
-                                      torch.from_numpy(adj_norm.indices.astype(np.int64)).to(dev),
-                                      torch.from_numpy(adj_norm.data.astype(np.float32)).to(dev), size=(n, n))
-        cur = hops[0]
-        for _ in range(3):
-            cur = torch.sparse.mm(a_t, hops[0])
-        torch.cuda.synchronize()
-        c_steps = max(3, min(args.steps, 10))
-        ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        ms = 0.0
-        for i in range(c_steps):
-            flush.fill_(i & 0xFF)
-            ev0.record(stream)
-            cur = hops[0]
-            for _ in range(K):
-                cur = torch.sparse.mm(a_t, cur)
-            ev1.record(stream)
-            torch.cuda.synchronize()
-            ms += ev0.elapsed_time(ev1)
-        err = float((cur - hops[K]).abs().max() / hops[K].abs().max())
-        comparators["cusparse_spmm_via_torch"] = {"value": nnz * K * c_steps / (ms / 1e3), "unit": UNIT,
-                                                   "us_per_hop": 1e3 * ms / (c_steps * K), "max_rel_diff_vs_ours": err,
-                                                   "note": "torch.sparse.mm on a CSR tensor (cuSPARSE SpMM), device resident, "
-                                                           "same graph and features; a library call, reported for context"}
-        del a_t, cur
-    except Exception as exc:  # the comparator must never break the bench line
-        comparators["cusparse_spmm_via_torch"] = {"unavailable": str(exc)[:200]}
-
-    cpu = None
-    if not args.no_cpu_baseline:
-        times, kind, threads = cpu_reference_steps(adj_norm, x_host.numpy(), K, steps=3, warmup=1, budget_s=25.0)
-        cpu = {"value": nnz * K * len(times) / float(np.sum(times)), "unit": UNIT, "cores": threads, "kind": kind,
-               "sample": f"full workload, {len(times)} steps of K={K} hops after 1 warm-up, bare kernel"}
-
-    # cut rows are folded inside the hop kernel (one launch per hop) unless the separate fold launch is selected
-    separate_fold = os.environ.get("SGLB200_FOLD", "kernel").startswith("f") or d > 512
-    launches_per_step = K * (1 + (1 if info["carry_runs"] > 0 and args.mode == "fast" and separate_fold else 0))
-    line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": 1, "steps": args.steps, "warmup": max(args.warmup, 3),
-            "ms_per_step": 1e3 * total_s / args.steps, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
-            "dtype": "f32", "data": "synthetic", "config": workload_config(name, n, nnz, d, K, args), "roofline": roofline,
-            "cpu_baseline": cpu, "e2e": e2e, "comparators": comparators, "clocks": clocks,
-            "gpu_launches": launches_per_step * args.steps,
-            "parity": {"checked": "every hop vs oracle fma chain on 2000 sampled rows", "max_rel_err": worst},
-            "setup": {"generate_s": t_gen, "normalise_host_scipy_s": t_norm, "build_on_device_s": t_upload,
-                      "tiles": info["tiles_fast"], "cut_rows": info["carry_runs"], "tile_items": info["tile_items"],
-                      "split_threshold": info["split_threshold"], "bytes_resident": info["bytes_resident"]}}
-    print(json.dumps(line))
+    except Exception as exc:
+        out["sgc_preprocess"] = {"error": str(exc)[:300]}
+    return out
 
 
-def device_graph(name, dev):
-    """Edges of the workload on the device: (rows, cols, n, d, K) with the symmetrisation the reference applies."""
+# ---------------------------------------------------------------------------------------------------------------
+# B200 arm, N GPUs: feature split (default) and row partition
+# ---------------------------------------------------------------------------------------------------------------
+def dist_setup():
     import torch
-    if name.startswith("rmat"):
-        scale = int(name[4:])
-        n, m, d, K = 1 << scale, 8 << scale, 128, 10
-    else:
-        n, m, scale, d, K = WORKLOADS[name]
-    seed = {"pubmed": 0, "arxiv": 1, "products": 2}.get(name, 4)
-    src, dst = rmat_edges(n, m, scale, seed, dev)
-    return torch.cat([src, dst]), torch.cat([dst, src]), n, d, K
+    import torch.distributed as dist
+    rank, world = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"])
+    local = int(os.environ.get("LOCAL_RANK", rank))
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    dist.init_process_group("nccl", device_id=dev)
+    return rank, world, local, dev
 
 
-def run_dist(args):
-    """N > 1: 1-D row partition of A^ (sgl_b200.dist), one process per GPU under torchrun, NCCL halo exchange per hop.
-    Strong scaling: the same graph as N = 1; value = nnz * K * steps / max-over-ranks device time."""
+def timed_steps(args, step, flush, rank, local, dev):
+    """W warm-up steps, then `steps` timed steps bracketed by barrier + synchronize; max over ranks of the device time."""
+    import torch
+    import torch.distributed as dist
+    for _ in range(max(args.warmup, 3)):
+        step()
+    torch.cuda.synchronize()
+    dist.barrier()
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+        time.sleep(0.2)
+    starts = [torch.cuda.Event(enable_timing=True) for _ in range(args.steps)]
+    stops = [torch.cuda.Event(enable_timing=True) for _ in range(args.steps)]
+    dist.barrier()
+    torch.cuda.synchronize()
+    wall0 = time.perf_counter()
+    for i in range(args.steps):
+        flush.fill_(i & 0xFF)
+        starts[i].record()
+        step()
+        stops[i].record()
+    torch.cuda.synchronize()
+    dist.barrier()
+    wall1 = time.perf_counter()
+    mine = torch.tensor([sum(s.elapsed_time(e) for s, e in zip(starts, stops)) / 1e3], device=dev, dtype=torch.float64)
+    dist.all_reduce(mine, op=dist.ReduceOp.MAX)
+    clocks = sampler.stop(wall0, wall1) if rank == 0 else None
+    return float(mine.item()), clocks
+
+
+def run_feature_split(args):
+    """N > 1, default: every GPU holds all of A^ (1.0 GB at products-shape, 17 GB at the 2-billion-edge config) and
+    propagates d / N feature columns -- column blocks of A^^k X are independent, so the K hops need NO exchange; the one
+    collective is an all-to-all of the last hop into row shards (N*d*4/world bytes per rank) inside the timed step."""
+    import torch
+    import torch.distributed as dist
+    from sgl_b200.dist import FeatureSplitOperator
+    from sgl_b200.graph_build import build_operator_device, parts_to_scipy
+
+    rank, world, local, dev = dist_setup()
+    name = args.workload or "products"
+    rows, cols, n, d, K = device_graph(name, dev)
+    if args.feat_dim > 0:
+        d = args.feat_dim
+    t0 = time.perf_counter()
+    op = build_operator_device(rows, cols, n, r=0.5, tile_items=args.tile_items, split_threshold=args.split_threshold)
+    torch.cuda.synchronize()
+    t_build = time.perf_counter() - t0
+    del rows, cols
+    nnz = int(op.nnz)
+    adj_norm = parts_to_scipy(op.parts) if rank == 0 else None
+    op.parts = None
+    torch.cuda.empty_cache()
+    fs = FeatureSplitOperator(world=world, rank=rank, operator=op, mode=args.mode)
+    cb = fs.column_bounds(d, world)
+    c0, c1 = int(cb[rank]), int(cb[rank + 1])
+    x_full = torch.randn(n, d, generator=torch.Generator().manual_seed(0))
+    x_pin = x_full[:, c0:c1].contiguous().pin_memory()
+    x_blk = x_pin.to(dev)
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
+    hops = [x_blk] + [torch.empty_like(x_blk) for _ in range(K)]
+    state = {}
+
+    def hops_only():
+        for k in range(1, K + 1):
+            op.spmm(hops[k - 1], out=hops[k], mode=args.mode)
+
+    def step():
+        hops_only()
+        state["rows"] = fs.rows_from_columns(hops[K], d)
+
+    total_s, clocks = timed_steps(args, step, flush, rank, local, dev)
+
+    # hops only (no final exchange), for the scaling analysis
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    dist.barrier()
+    ev0.record()
+    for _ in range(3):
+        hops_only()
+    ev1.record()
+    torch.cuda.synchronize()
+    hop_only = torch.tensor([ev0.elapsed_time(ev1) / 3e3], device=dev, dtype=torch.float64)
+    dist.all_reduce(hop_only, op=dist.ReduceOp.MAX)
+
+    # end to end at N GPUs: pinned host column block in -> K hops -> all-to-all -> this rank's rows of hop K to pinned host
+    e2e = None
+    if not args.no_e2e:
+        rb = fs.row_bounds(n, world)
+        y_pin = torch.empty((int(rb[rank + 1] - rb[rank]), d), dtype=torch.float32, pin_memory=True)
+        e2e_steps = max(3, min(args.steps, 10))
+
+        def e2e_step():
+            hops[0].copy_(x_pin, non_blocking=True)
+            step()
+            y_pin.copy_(state["rows"], non_blocking=True)
+            torch.cuda.current_stream().synchronize()
+
+        for _ in range(2):
+            e2e_step()
+        dist.barrier()
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        for _ in range(e2e_steps):
+            e2e_step()
+        torch.cuda.synchronize()
+        dt = torch.tensor([time.perf_counter() - t0], device=dev, dtype=torch.float64)
+        dist.all_reduce(dt, op=dist.ReduceOp.MAX)
+        e2e = {"value": nnz * K * e2e_steps / float(dt.item()), "unit": UNIT, "h2d_bytes_per_step": n * d * 4,
+               "d2h_bytes_per_step": n * d * 4, "ms_per_step": 1e3 * float(dt.item()) / e2e_steps, "steps": e2e_steps,
+               "api": "per rank: pinned host column block of X in -> K hops on the replicated A^ -> all-to-all into row shards -> "
+                      "this rank's rows of hop K to pinned host (bytes are whole-job totals)"}
+
+    # parity on rank 0: (1) every hop of its column block vs the oracle on sampled rows, (2) EXACT mode: the narrow-row
+    # kernel's block equals the same columns of a full-width single-GPU hop bit for bit
+    parity = None
+    if rank == 0:
+        rng = np.random.default_rng(1)
+        sample = np.sort(rng.choice(n, min(n, 2000), replace=False))
+        sub = adj_norm[sample].astype(np.float32)
+        sample_t = torch.from_numpy(sample).to(dev)
+        worst = 0.0
+        hops[0].copy_(x_pin)
+        hops_only()
+        for k in range(1, K + 1):
+            ref = oracle_rows(sub, hops[k - 1].cpu().numpy(), c1 - c0)
+            got = hops[k][sample_t].cpu().numpy()
+            worst = max(worst, float(np.abs(got - ref).max() / max(np.abs(ref).max(), 1e-30)))
+        x_dev_full = x_full.to(dev)
+        full = op.spmm(x_dev_full, mode="exact")
+        blk = op.spmm(hops[0], mode="exact")
+        bit_equal = bool(torch.equal(full[:, c0:c1], blk))
+        del full, blk, x_dev_full
+        parity = {"checked": "rank 0 column block: every hop vs oracle fma chain on 2000 sampled rows; EXACT-mode block vs the "
+                             "same columns of a full-width single-GPU hop", "max_rel_err": worst,
+                  "exact_mode_bit_equal_to_single_gpu": bit_equal}
+        assert worst <= 1e-5 and bit_equal, parity
+        value = nnz * K * args.steps / total_s
+        hop_s = float(hop_only.item()) / K
+        peak, src = hbm_peak()
+        b_alg = algorithmic_bytes_per_hop(n, nnz, d)
+        achieved = b_alg / hop_s / 1e9
+        widths = [int(cb[q + 1] - cb[q]) for q in range(world)]
+        line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
+                "warmup": max(args.warmup, 3), "ms_per_step": 1e3 * total_s / args.steps, "higher_is_better": True,
+                "scaling": "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+                "config": workload_config(name, n, nnz, d, K, args),
+                "partition": f"feature split x{world}: A^ replicated, column blocks {widths}, no per-hop exchange, one "
+                             "all-to-all of hop K into row shards per step",
+                "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak * world, "unit": "GB/s",
+                             "frac": achieved / (peak * world), "traffic": None,
+                             "kernel": "spmm_group_kernel" if max(widths) <= 64 else "spmm_flat_kernel",
+                             "algorithmic_bytes_per_launch": b_alg / world, "us_per_launch": hop_s * 1e6,
+                             "note": "whole-job algorithmic bytes of the single-GPU hop / (hop time x N x peak); every rank "
+                                     "also streams the full index structure (8 nnz bytes), which the algorithmic count charges once",
+                             "peak_source": src + " x n_gpus"},
+                "cpu_baseline": None, "e2e": e2e, "clocks": clocks, "gpu_launches": args.steps * K * world,
+                "parity": parity,
+                "timing": {"hops_only_ms_per_step": 1e3 * float(hop_only.item()),
+                           "exchange_ms_per_step": 1e3 * (total_s / args.steps - float(hop_only.item()))},
+                "setup": {"build_on_device_s": t_build}}
+        print(json.dumps(line))
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+def run_row_partition(args):
+    """N > 1, `--partition row`: 1-D row partition of A^ (sgl_b200.dist), halo exchange per hop."""
     import torch
     import torch.distributed as dist
     from sgl_b200.dist import DistOperator, build_plan, exchange_volume_bytes
     from sgl_b200.graph_build import normalized_adjacency_device, values_from_parts
 
-    rank, world = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"])
+    rank, world, local, dev = dist_setup()
     os.environ["SGLB200_DIST_TRANSPORT"] = args.transport
-    local = int(os.environ.get("LOCAL_RANK", rank))
-    torch.cuda.set_device(local)
-    dev = torch.device("cuda", local)
-    dist.init_process_group("nccl", device_id=dev)
-    name = args.workload or "arxiv"
+    name = args.workload or "products"
     rows, cols, n, d, K = device_graph(name, dev)
-    if args.partition == "feature":
-        return run_feature_split(args, rank, world, local, dev, name, rows, cols, n, d, K)
     t0 = time.perf_counter()
     parts = normalized_adjacency_device(rows, cols, n, None, r=0.5, alpha=None, pow_on="host")
     del rows, cols
@@ -509,34 +857,9 @@ def run_dist(args):
     def step():
         return op.propagate(x_local, K, keep="last")
 
-    for _ in range(max(args.warmup, 3)):
-        step()
-    torch.cuda.synchronize()
-    dist.barrier()
-    sampler = ClockSampler(local)
-    if rank == 0:
-        sampler.start()
-        time.sleep(0.2)
-    starts = [torch.cuda.Event(enable_timing=True) for _ in range(args.steps)]
-    stops = [torch.cuda.Event(enable_timing=True) for _ in range(args.steps)]
-    dist.barrier()
-    torch.cuda.synchronize()
-    wall0 = time.perf_counter()
-    for i in range(args.steps):
-        flush.fill_(i & 0xFF)
-        starts[i].record()
-        outs = step()
-        stops[i].record()
-    torch.cuda.synchronize()
-    dist.barrier()
-    wall1 = time.perf_counter()
-    mine = torch.tensor([sum(s.elapsed_time(e) for s, e in zip(starts, stops)) / 1e3], device=dev, dtype=torch.float64)
-    dist.all_reduce(mine, op=dist.ReduceOp.MAX)
-    total_s = float(mine.item())
+    total_s, clocks = timed_steps(args, step, flush, rank, local, dev)
     recv = torch.tensor([float(exchange_volume_bytes(plan, d))], device=dev, dtype=torch.float64)
     dist.all_reduce(recv, op=dist.ReduceOp.MAX)
-    # end to end at N GPUs: every rank uploads its row shard of X from pinned host memory, the K partitioned hops run,
-    # and the rank's rows of the last hop (what SGC's LastMessageOp consumes) come back into pinned host memory
     e2e = None
     if not args.no_e2e:
         x_pin = x_full[lo:hi].clone().pin_memory()
@@ -563,81 +886,26 @@ def run_dist(args):
                "d2h_bytes_per_step": n * d * 4, "ms_per_step": 1e3 * float(dt.item()) / e2e_steps, "steps": e2e_steps,
                "api": "DistOperator.propagate per rank: pinned host row shard in -> K partitioned hops -> pinned host rows "
                       "of hop K out (bytes are whole-job totals)"}
-    # parity: this rank's last hop against the oracle chain on sampled local rows, computed from the full input
-    ok = 1.0
     if rank == 0:
-        clocks = sampler.stop(wall0, wall1)
         value = nnz * K * args.steps / total_s
         hop_s = total_s / (args.steps * K)
-        try:
-            peak = float(json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))["hbm_gbs"])
-            src = "MEASURED_PEAKS.json hbm_gbs"
-        except Exception:
-            peak, src = 6650.0, "fallback (B200_PROFILING.md)"
+        peak, src = hbm_peak()
         b_alg = algorithmic_bytes_per_hop(n, nnz, d)
         achieved = b_alg / hop_s / 1e9
+        # per rank and hop: n_chunks hop launches; peer transport adds (world-1) row pushes per chunk + signal + wait
+        per_hop = n_chunks + ((world - 1) * n_chunks + 2 if op.transport == "peer" else 1)
         line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
                 "warmup": max(args.warmup, 3), "ms_per_step": 1e3 * total_s / args.steps, "higher_is_better": True,
                 "scaling": "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-                "config": dict(workload_config(name, n, nnz, d, K, args), exchange=args.exchange, chunks=n_chunks,
-                               transport=op.transport,
-                               halo_recv_bytes_per_hop_max_rank=float(recv.item())),
+                "config": workload_config(name, n, nnz, d, K, args),
+                "partition": f"1-D row partition x{world}, exchange={args.exchange}, transport={op.transport}, chunks={n_chunks}, "
+                             f"halo_recv_bytes_per_hop_max_rank={float(recv.item()):.0f}",
                 "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak * world, "unit": "GB/s",
                              "frac": achieved / (peak * world), "traffic": None, "kernel": "spmm_flat_kernel",
                              "algorithmic_bytes_per_launch": b_alg / world, "us_per_launch": hop_s * 1e6,
                              "peak_source": src + " x n_gpus"},
-                "cpu_baseline": None,
-                "e2e": e2e, "clocks": clocks, "gpu_launches": args.steps * K * 3,
+                "cpu_baseline": None, "e2e": e2e, "clocks": clocks, "gpu_launches": args.steps * K * per_hop * world,
                 "setup": {"build_plan_s": t_build}}
-        print(json.dumps(line))
-    dist.destroy_process_group()
-
-
-def run_feature_split(args, rank, world, local, dev, name, rows, cols, n, d, K):
-    """N > 1, alternative partition: every GPU holds all of A^ and propagates d / N feature columns; the only collective
-    is one all-gather of the last hop's column blocks inside the timed step."""
-    import torch
-    import torch.distributed as dist
-    from sgl_b200.dist import FeatureSplitOperator
-    from sgl_b200.graph_build import build_operator_device
-
-    t0 = time.perf_counter()
-    op = build_operator_device(rows, cols, n, r=0.5)
-    nnz = int(op.nnz)
-    op.parts = None
-    t_build = time.perf_counter() - t0
-    fs = FeatureSplitOperator(world=world, rank=rank, operator=op, mode=args.mode)
-    cb = fs.column_bounds(d, world)
-    x_full = torch.randn(n, d, generator=torch.Generator().manual_seed(0))
-    x_blk = x_full[:, int(cb[rank]):int(cb[rank + 1])].contiguous().to(dev)
-    flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
-
-    def step():
-        return fs.gather_columns(fs.propagate(x_blk, K)[-1], d)
-
-    for _ in range(max(args.warmup, 3)):
-        step()
-    torch.cuda.synchronize()
-    dist.barrier()
-    starts = [torch.cuda.Event(enable_timing=True) for _ in range(args.steps)]
-    stops = [torch.cuda.Event(enable_timing=True) for _ in range(args.steps)]
-    for i in range(args.steps):
-        flush.fill_(i & 0xFF)
-        starts[i].record()
-        step()
-        stops[i].record()
-    torch.cuda.synchronize()
-    dist.barrier()
-    mine = torch.tensor([sum(s.elapsed_time(e) for s, e in zip(starts, stops)) / 1e3], device=dev, dtype=torch.float64)
-    dist.all_reduce(mine, op=dist.ReduceOp.MAX)
-    total_s = float(mine.item())
-    if rank == 0:
-        line = {"metric": METRIC, "value": nnz * K * args.steps / total_s, "unit": UNIT, "n_gpus": world,
-                "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": 1e3 * total_s / args.steps,
-                "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-                "config": dict(workload_config(name, n, nnz, d, K, args), partition=f"feature split x{world} (A^ replicated)"),
-                "roofline": None, "cpu_baseline": None, "e2e": None, "clocks": None, "gpu_launches": args.steps * K,
-                "setup": {"build_on_device_s": t_build}}
         print(json.dumps(line))
     dist.destroy_process_group()
 
@@ -648,7 +916,6 @@ def main():
         # torchrun exports OMP_NUM_THREADS=1; the reference arm is meant to use every host core it can, and libgomp reads
         # the variable when it is loaded (before torch / the oracle library are imported below)
         os.environ["OMP_NUM_THREADS"] = str(os.cpu_count() or 1)
-    if args.impl == "reference":
         run_reference(args)
     else:
         run_b200(args)

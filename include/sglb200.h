@@ -142,6 +142,12 @@ SGLB200_API int sglb200_propagate_fused(sglb200_graph_t g, const float *X, int64
                             int d, int K, int mode, int agg_op, int agg_start, int agg_end, const float *agg_weights,
                             float *agg_out, int64_t ld_out, int fuse_norm, void *stream);
 
+/* ---- f3: one label-propagation layer (tricks/utils.py:54-56) as ONE hop:  Y = clamp(alpha * (A X) + res, lo, hi) with the
+ * scale, the residual add and the clamp in the hop kernel's row flush (res: [n, d] device or NULL; do_clamp == 0: no
+ * clamp).  Arithmetic as the reference's torch expression: separately rounded multiply and add.  d <= 512. */
+SGLB200_API int sglb200_spmm_axpby(sglb200_graph_t g, const float *X, int64_t ldx, float *Y, int64_t ldy, int d, int mode,
+                       float alpha, const float *res, int64_t ld_res, int do_clamp, float lo, float hi, void *stream);
+
 /* same with host buffers: uploads X (host [n,d] contiguous), runs K hops on the device, downloads hop k into
  * hops_out[k-1] (k = 1..K; NULL entries are skipped, e.g. keep only the last hop).  Synchronous. */
 SGLB200_API int sglb200_propagate_host(sglb200_graph_t g, const float *X, float *const *hops_out, int d, int K, int mode);
@@ -171,6 +177,23 @@ SGLB200_API int sglb200_lw_backward(int kind, const float *const *feats, int n_a
                         const float *grad_out, float *const *grad_feats, float *grad_w, float *grad_bias,
                         float *scratch, void *stream);
 
+/* ---- a12: IterateLearnableWeightedMessageOp ("recursive") fused forward / backward, ProjectedConcat epilogue ----------
+ * (iterate_learnable_weighted_message_op.py:28-51, projected_concat_message_op.py:19-28).
+ * feats: n_hops device pointers [B, d] contiguous -- the hops [start, end) the op combines (n_hops <= 16); w: 2d floats
+ * [w_a | w_b] of the Linear(2d -> 1), bias: 1 float (device).  forward writes dots [B, 2*n_hops] (kept for the backward),
+ * hop_w [B, n_hops] (the final weights) and out [B, d]; backward ACCUMULATES into grad_feats[k] [B, d], grad_w (2d) and
+ * grad_bias (1): the caller zeroes them. */
+SGLB200_API int sglb200_it_forward(const float *const *feats, int n_hops, int64_t B, int d, const float *w, const float *bias,
+                       float *dots, float *hop_w, float *out, void *stream);
+SGLB200_API int sglb200_it_backward(const float *const *feats, int n_hops, int64_t B, int d, const float *w, const float *bias,
+                        const float *dots, const float *grad_out, float *const *grad_feats, float *grad_w,
+                        float *grad_bias, void *stream);
+/* out [B, n_hops*h]: column block k = ys[k] (k == 0) or relu(ys[k]) (k > 0), ys[k] [B, h] contiguous; the backward writes
+ * grad_ys[k] = grad_out block k (masked by ys[k] > 0 for k > 0). */
+SGLB200_API int sglb200_relu_concat(const float *const *ys, int n_hops, int64_t B, int h, float *out, void *stream);
+SGLB200_API int sglb200_relu_concat_backward(const float *const *ys, int n_hops, int64_t B, int h, const float *grad_out,
+                                 float *const *grad_ys, void *stream);
+
 /* ---- f1: device-resident feature store: out[b, :] = feat[idx[b], :] for every hop in one launch --------------
  * (models/base_model.py:58-61 does a CPU fancy-index + H2D per step).  idx: B int64 on the device. */
 SGLB200_API int sglb200_gather_rows(const float *const *feats, int n_feats, int64_t ld_in, const int64_t *idx, int64_t B, int d,
@@ -191,6 +214,10 @@ SGLB200_API int sglb200_push_rows(const float *src, int64_t ld_src, int d, const
                       int64_t ld_dst, int max_blocks, void *stream);
 SGLB200_API int sglb200_signal_peers(unsigned long long *const *flag_ptrs_dev, int n, unsigned long long value, void *stream);
 SGLB200_API int sglb200_wait_flags(const unsigned long long *flags_dev, int n, unsigned long long value, void *stream);
+/* wait_flags never spins forever: after SGLB200_PEER_TIMEOUT_MS (default 30000) it gives up and raises an error word that
+ * the next sglb200_wait_flags reports as SGLB200_ERR_CUDA; sglb200_peer_status returns (and clears) the mask of flag
+ * slots that timed out on the current device, 0 when none. */
+SGLB200_API int sglb200_peer_status(void);
 
 /* ---- legacy ABI: drop-in for the reference's two shared objects ----------------------------------------------
  * Same symbols, same signatures, host pointers, `answer` is accumulated into (matmul.c:36-37).  Internally:

@@ -36,10 +36,27 @@ for d in (128, 100, 47):
         aggregate(code, hops)
     aggregate(_lib.AGG_WEIGHTED, hops, [0.5, 0.25, 0.125, 0.0625])
     gather_rows(hops, torch.arange(0, n, 7, device="cuda"))
+    # round 2 kernels: fused driver (in-kernel fold + fused flush), lane-group kernel, TMA-staged kernel
+    for agg in ("mean", "max", "osd", "concat", "last"):
+        op.propagate_fused(x, 3, mode="fast", keep="none", agg=agg)
+    if d % 4 == 0:
+        xn = x[:, :16].contiguous()
+        assert torch.allclose(op.spmm(xn, mode="fast"), op.spmm(xn, mode="exact"), rtol=1e-4, atol=1e-5)
+        os.environ["SGLB200_TMA"] = "1"
+        y_tma = op.spmm(x, mode="fast")
+        os.environ.pop("SGLB200_TMA")
+        assert torch.allclose(y_tma, y_exact, rtol=1e-4, atol=1e-5)
     op.close()
 feats = [torch.randn(64, 16, device="cuda", requires_grad=True) for _ in range(4)]
 for kind, args in (("gate", (16,)), ("ori_ref", (16,)), ("jk", (3, 16))):
     lw = LearnableWeightedMessageOp(0, 4, kind, *args).cuda()
     lw.aggregate(feats).sum().backward()
+from sgl_b200.graph_build import operator_from_scipy_device  # noqa: E402
+from sgl_b200.operators.message_op import IterateLearnableWeightedMessageOp  # noqa: E402
+opd = operator_from_scipy_device(adj, r=0.5, alpha=0.15, tile_items=32, split_threshold=8)   # fused normalisation + PPR
+opd.propagate_fused(torch.randn(n, 100, device="cuda"), 3, mode="fast", keep="all", agg="mean")
+opd.close()
+it = IterateLearnableWeightedMessageOp(0, 4, "recursive", 16).cuda()
+it.aggregate(feats).sum().backward()
 torch.cuda.synchronize()
 print("sanitize smoke ok")

@@ -37,6 +37,8 @@ SIGNATURES = {
     "sglb200_propagate": (c_int, [c_void_p, POINTER(c_void_p), c_int64, c_int, c_int, c_int, c_void_p]),
     "sglb200_propagate_fused": (c_int, [c_void_p, c_void_p, c_int64, POINTER(c_void_p), c_int64, c_int, c_int, c_int, c_int,
                                         c_int, c_int, POINTER(c_float), c_void_p, c_int64, c_int, c_void_p]),
+    "sglb200_spmm_axpby": (c_int, [c_void_p, c_void_p, c_int64, c_void_p, c_int64, c_int, c_int, c_float, c_void_p, c_int64,
+                                   c_int, c_float, c_float, c_void_p]),
     "sglb200_propagate_host": (c_int, [c_void_p, c_void_p, POINTER(c_void_p), c_int, c_int, c_int]),
     "sglb200_aggregate": (c_int, [c_int, POINTER(c_void_p), c_int, c_int64, c_int, c_int64, POINTER(c_float), c_void_p,
                                   c_int64, c_void_p]),
@@ -45,6 +47,12 @@ SIGNATURES = {
     "sglb200_lw_backward": (c_int, [c_int, POINTER(c_void_p), c_int, c_int, c_int, c_int64, c_int, c_void_p, c_void_p,
                                     c_void_p, c_void_p, c_void_p, POINTER(c_void_p), c_void_p, c_void_p, c_void_p,
                                     c_void_p]),
+    "sglb200_it_forward": (c_int, [POINTER(c_void_p), c_int, c_int64, c_int, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p,
+                                   c_void_p]),
+    "sglb200_it_backward": (c_int, [POINTER(c_void_p), c_int, c_int64, c_int, c_void_p, c_void_p, c_void_p, c_void_p,
+                                    POINTER(c_void_p), c_void_p, c_void_p, c_void_p]),
+    "sglb200_relu_concat": (c_int, [POINTER(c_void_p), c_int, c_int64, c_int, c_void_p, c_void_p]),
+    "sglb200_relu_concat_backward": (c_int, [POINTER(c_void_p), c_int, c_int64, c_int, c_void_p, POINTER(c_void_p), c_void_p]),
     "sglb200_gather_rows": (c_int, [POINTER(c_void_p), c_int, c_int64, c_void_p, c_int64, c_int, POINTER(c_void_p),
                                     c_int64, c_void_p]),
     "sglb200_ipc_alloc": (c_int, [c_int64, POINTER(c_void_p), c_void_p]),
@@ -54,6 +62,7 @@ SIGNATURES = {
     "sglb200_push_rows": (c_int, [c_void_p, c_int64, c_int, c_void_p, c_int64, c_void_p, c_int64, c_int, c_void_p]),
     "sglb200_signal_peers": (c_int, [c_void_p, c_int, ctypes.c_uint64, c_void_p]),
     "sglb200_wait_flags": (c_int, [c_void_p, c_int, ctypes.c_uint64, c_void_p]),
+    "sglb200_peer_status": (c_int, []),
     "FloatCSRMulDenseOMP": (None, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int]),
     "FloatCSRMulDense": (c_int, [c_void_p, c_int, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int]),
 }

@@ -9,6 +9,8 @@
 // serialises on its own stream (2.2 ms per hop for 417 MB), NVLink peer stores are limited by the link (~700 GB/s).
 #include <string.h>
 
+#include <stdlib.h>
+
 #include "common.cuh"
 
 namespace sglb200 {
@@ -55,15 +57,28 @@ __global__ void signal_peers_kernel(unsigned long long *const *flag_ptrs, int n,
     asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(flag_ptrs[i]), "l"(value) : "memory");
 }
 
-// spins until every one of the n local flag words has reached `value`
-__global__ void wait_flags_kernel(const unsigned long long *flags, int n, unsigned long long value)
+// spins until every one of the n local flag words has reached `value` -- but never forever: a peer that died would
+// otherwise hang this GPU.  After `timeout_ns` (globaltimer) the kernel gives up and raises the error word, which the
+// next sglb200_wait_flags / sglb200_peer_status call reports (the hop results of that step are then undefined).
+__global__ void wait_flags_kernel(const unsigned long long *flags, int n, unsigned long long value,
+                                  unsigned long long timeout_ns, unsigned int *error_word)
 {
     const int i = threadIdx.x;
     if (i < n) {
-        unsigned long long seen;
+        unsigned long long seen, t0, t1;
+        asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t0));
+        unsigned int polls = 0;
         do {
             asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(seen) : "l"(flags + i) : "memory");
-        } while (seen < value);
+            if (seen >= value) break;
+            if ((++polls & 1023u) == 0) {
+                asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t1));
+                if (t1 - t0 > timeout_ns) {
+                    atomicOr(error_word, 1u << (i & 31));
+                    break;
+                }
+            }
+        } while (true);
     }
     __syncthreads();
 }
@@ -151,14 +166,55 @@ int sglb200_signal_peers(unsigned long long *const *flag_ptrs_dev, int n, unsign
     return SGLB200_OK;
 }
 
+// per-device error word of the flag waits (mapped pinned host memory: readable without synchronising the device)
+static unsigned int *peer_error_word(int create)
+{
+    static unsigned int *words[64] = {nullptr};
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64) return nullptr;
+    if (!words[dev] && create) {
+        unsigned int *w = nullptr;
+        if (cudaHostAlloc(&w, sizeof(unsigned int), cudaHostAllocMapped | cudaHostAllocPortable) != cudaSuccess) {
+            (void)cudaGetLastError();
+            return nullptr;
+        }
+        *w = 0;
+        words[dev] = w;
+    }
+    return words[dev];
+}
+
 int sglb200_wait_flags(const unsigned long long *flags_dev, int n, unsigned long long value, void *stream)
 {
     clear_error();
     SGL_REQUIRE(n >= 0 && n <= 1024 && (n == 0 || flags_dev), "wait_flags: bad argument");
     if (n == 0) return SGLB200_OK;
-    wait_flags_kernel<<<1, 32 * ((n + 31) / 32), 0, (cudaStream_t)stream>>>(flags_dev, n, value);
+    unsigned int *err = peer_error_word(1);
+    SGL_REQUIRE(err != nullptr, "wait_flags: cannot allocate the error word");
+    if (*err != 0) {
+        set_error("wait_flags: an earlier wait timed out (peer mask 0x%x): a peer rank is dead or stalled", *err);
+        return SGLB200_ERR_CUDA;
+    }
+    static unsigned long long timeout_ns = 0;
+    if (timeout_ns == 0) {
+        const char *e = getenv("SGLB200_PEER_TIMEOUT_MS");
+        timeout_ns = (unsigned long long)(e ? atoll(e) : 30000) * 1000000ULL;   // default 30 s
+    }
+    unsigned int *err_dev = nullptr;
+    SGL_CUDA_CHECK(cudaHostGetDevicePointer(&err_dev, err, 0));
+    wait_flags_kernel<<<1, 32 * ((n + 31) / 32), 0, (cudaStream_t)stream>>>(flags_dev, n, value, timeout_ns, err_dev);
     SGL_CUDA_CHECK(cudaGetLastError());
     return SGLB200_OK;
+}
+
+/* 0 when no flag wait has timed out on the current device, else the mask of flag slots that did (and clears it) */
+int sglb200_peer_status(void)
+{
+    unsigned int *err = peer_error_word(0);
+    if (!err) return 0;
+    const int v = (int)*err;
+    *err = 0;
+    return v;
 }
 
 }  // extern "C"

@@ -9,9 +9,11 @@
 //     (utils.py:76-88:  A^ = diag(dL) (A+I)^T diag(dR));  PPR's teleport term alpha*x_i is added in the same flush;
 //   * stores hop k only where the caller wants it (a model that aggregates needs none of the intermediate hops);
 //   * writes the next hop's input (pre-scaled) into an internal ping-pong slab;
-//   * folds the row into the running aggregate: sum / mean / weighted / max / min in the reference's left-to-right order
-//     (bit-exact), concat by storing into the hop's column block, NAFS over-smoothing-distance weights by a one-pass
-//     softmax (|cos| <= 1 needs no max shift).
+//   * folds the row into the running aggregate: sum / mean / weighted as ONE fire-and-forget L2 reduction per row
+//     (red.global.add.v4.f32 -- no read, no stall; one IEEE add per element per hop in hop order = the reference's
+//     left-to-right sum), concat / last by storing into the right place, max / min / NAFS over-smoothing-distance weights
+//     by a read-modify-write in the flush (correct, but each row waits for its read: the host picks the separate
+//     aggregation kernels for those where that is faster, see sgl_b200/sgap.py).
 // Algorithmic bytes per hop fall from  8 nnz + 8 N d  (+ (K'+1) 4 N d for the separate aggregation pass) to
 // 4..8 nnz + 8 N d + 8 N d (aggregate read-modify-write), with no aggregation pass at all.
 #include <math.h>
@@ -31,6 +33,17 @@ __global__ void __launch_bounds__(256) scale_rows_kernel(const float *__restrict
         const int col = (int)(i - row * d);
         const float v = in[row * ld_in + col];
         out[row * ld_out + col] = scale ? __fmul_rn(v, scale[row]) : v;
+    }
+}
+
+// agg[i, :] /= div  (mean: ONE true division after the left-to-right sum, mean_message_op.py:10)
+__global__ void __launch_bounds__(256) divide_rows_kernel(float *__restrict__ agg, int64_t ld, int64_t n, int d, float div)
+{
+    const int64_t total = n * d;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+        const int64_t row = i / d;
+        const int col = (int)(i - row * d);
+        agg[row * ld + col] = __fdiv_rn(agg[row * ld + col], div);
     }
 }
 
@@ -111,6 +124,24 @@ using namespace sglb200;
 
 extern "C" {
 
+int sglb200_spmm_axpby(sglb200_graph_t g, const float *X, int64_t ldx, float *Y, int64_t ldy, int d, int mode, float alpha,
+                       const float *res, int64_t ld_res, int do_clamp, float lo, float hi, void *stream)
+{
+    clear_error();
+    SGL_REQUIRE(g && X && Y, "spmm_axpby: NULL argument");
+    SGL_REQUIRE(alpha != 0.0f, "spmm_axpby: alpha must be non-zero");
+    SGL_REQUIRE(d >= 0 && d <= 512, "spmm_axpby: feature widths up to 512");
+    SGL_REQUIRE(!res || ld_res >= d, "spmm_axpby: ld_res too small");
+    Epilogue e = {};
+    e.acc_scale = alpha;
+    e.add_rows = res;
+    e.ld_add = ld_res;
+    e.clamp = do_clamp;
+    e.clamp_lo = lo;
+    e.clamp_hi = hi;
+    return spmm_launch_ex(g, X, ldx, Y, ldy, d, mode, 0, 0, -1, &e, 0, (cudaStream_t)stream);
+}
+
 int sglb200_propagate_fused(sglb200_graph_t g, const float *X, int64_t ldx, float *const *hops_out, int64_t ld_hops, int d, int K,
                             int mode, int agg_op, int agg_start, int agg_end, const float *agg_weights, float *agg_out,
                             int64_t ld_out, int fuse_norm, void *stream_)
@@ -185,6 +216,11 @@ int sglb200_propagate_fused(sglb200_graph_t g, const float *X, int64_t ldx, floa
             epi_op == EPI_AGG_OSD && K == 0);
         SGL_CUDA_CHECK(cudaGetLastError());
     }
+    const bool running_sum = epi_op == EPI_AGG_SUM || epi_op == EPI_AGG_WEIGHTED;
+    if (running_sum && first >= 1) {
+        // no hop-0 term: start from zeros so that every included hop is a pure add (0 + f_s = f_s exactly, like python's sum())
+        SGL_CUDA_CHECK(cudaMemset2DAsync(agg_out, (size_t)ld_out * sizeof(float), 0, (size_t)d * sizeof(float), (size_t)n, stream));
+    }
     const float *in = X;
     int64_t ld_in = ldx;
     if (fused && K > 0) {
@@ -237,9 +273,9 @@ int sglb200_propagate_fused(sglb200_graph_t g, const float *X, int64_t ldx, floa
         }
         if (epi_op != EPI_AGG_NONE && k >= first && k <= last) {
             e.agg_op = epi_op;
-            e.agg_init = (k == first) ? 1 : 0;     // first > 0 here: hop 0 was folded by agg_init_kernel
+            e.agg_init = (k == first && !running_sum) ? 1 : 0;   // first > 0 here (hop 0: agg_init_kernel); running sums start from zeros
             e.agg_w = agg_weights ? agg_weights[k] : 1.0f;
-            e.agg_div = (k == last) ? mean_div : 0.0f;
+            e.agg_div = 0.0f;   // mean: the running sum uses L2 reductions (no read); the division is one light pass at the end
             e.agg = agg_out;
             e.ld_agg = ld_out;
             if (epi_op == EPI_AGG_OSD) {
@@ -260,6 +296,13 @@ int sglb200_propagate_fused(sglb200_graph_t g, const float *X, int64_t ldx, floa
         if (st != SGLB200_OK) return st;
         in = next_in;
         ld_in = ld_next;
+    }
+    if (mean_div != 0.0f && last >= 1) {
+        const int64_t total = n * d;
+        int64_t blocks = (total + 255) / 256;
+        if (blocks > 148 * 32) blocks = 148 * 32;
+        divide_rows_kernel<<<(unsigned)blocks, 256, 0, stream>>>(agg_out, ld_out, n, d, mean_div);
+        SGL_CUDA_CHECK(cudaGetLastError());
     }
     return SGLB200_OK;
 }

@@ -32,7 +32,7 @@ namespace sglb200 {
 // FLAG: the column stream is the tagged one (idx_tag: bit 31 = last non-zero of its row; graphs without empty rows), so a
 // row ends where the stream says so: no row-pointer window, no countdown -- fewer live registers, more resident warps.
 template <int VEC, int VPL, int U, bool ACCUM, int MINB, int PIPE, bool HINT = false, bool EPI = false, bool FLAG = false>
-__global__ void __launch_bounds__(kWarpsPerBlock * 32, MINB) spmm_flat_kernel(const SpmmParams p, const int32_t *__restrict__ idx_tag)
+__global__ void __launch_bounds__(kWarpsPerBlock * 32, MINB) spmm_flat_kernel(const __grid_constant__ SpmmParams p, const int32_t *__restrict__ idx_tag)
 {
     static_assert(!(FLAG && ACCUM), "the flagged walk starts every chain from zero");
     static_assert(!(EPI && ACCUM), "the fused row flush starts every chain from zero");
@@ -70,6 +70,12 @@ __global__ void __launch_bounds__(kWarpsPerBlock * 32, MINB) spmm_flat_kernel(co
         asm volatile("" : "+l"(xbase[v]));  // materialise: keeps the compiler from re-adding the parameter every load
         asm volatile("" : "+l"(ybase[v]));
     }
+    // lean flush with a running aggregate: the first flushed row of a tile that FINISHES a cut row is only a piece of that
+    // row -- the aggregate gets the folded row from whoever completes the fold, not this piece
+    bool red_skip_first = false;
+    if constexpr (!EPI) {
+        if (p.red_agg && p.fold) red_skip_first = p.head_run[t] >= 0;
+    }
     // fused row flush: a tile whose first row continues a cut row parks that piece in the workspace (slot after the
     // row's carriers) instead of flushing it; the tile that completes the row's arrivals performs the one real flush
     int cont_slot = -1;
@@ -83,6 +89,7 @@ __global__ void __launch_bounds__(kWarpsPerBlock * 32, MINB) spmm_flat_kernel(co
     const uint32_t ldy_bytes = (uint32_t)p.ldy * (uint32_t)sizeof(float);
     Slice<VEC> acc[VPL];
 
+    RowPrefetch<VEC, EPI ? VPL : 1> pf;   // fused flush: what the flush of the CURRENT row will read (fetched at row start)
     auto init_acc = [&](int r) {
 #pragma unroll
         for (int v = 0; v < VPL; ++v) {
@@ -90,6 +97,9 @@ __global__ void __launch_bounds__(kWarpsPerBlock * 32, MINB) spmm_flat_kernel(co
             if (ACCUM) {
                 if (act[v] && r < n_rows) acc[v].load(ybase[v] + (uint64_t)(uint32_t)r * ldy_bytes);
             }
+        }
+        if constexpr (EPI) {
+            if (r < n_rows) prefetch_row<VEC, VPL>(p, (uint32_t)r, act, cofs_v, pf);
         }
     };
 
@@ -112,6 +122,9 @@ __global__ void __launch_bounds__(kWarpsPerBlock * 32, MINB) spmm_flat_kernel(co
         init_acc(starts_here ? row : n_rows);
     } else {
         init_acc(n_rows);
+        if constexpr (EPI) {
+            if (row < n_rows) prefetch_row<VEC, VPL>(p, (uint32_t)row, act, cofs_v, pf);   // init_acc(n_rows) fetched nothing
+        }
     }
 
     auto flush_row = [&]() {
@@ -123,7 +136,10 @@ __global__ void __launch_bounds__(kWarpsPerBlock * 32, MINB) spmm_flat_kernel(co
                     if (act[v]) acc[v].store(wrow + (size_t)cofs_v[v] * sizeof(float));
                 cont_slot = -1;
             } else {
-                emit_row<VEC, VPL, 32>(p, (uint32_t)row, acc, act, cofs_v, kFull);
+                AccPack<VEC, VPL> pack;
+#pragma unroll
+                for (int v = 0; v < VPL; ++v) pack.s[v] = acc[v];
+                emit_row_call<VEC, VPL, 32>(&p, (uint32_t)row, pack, cofs_v[0], kFull, pf.row_scale, pf.z_scale, pf.self_coef);
             }
         } else {
 #pragma unroll
@@ -131,7 +147,9 @@ __global__ void __launch_bounds__(kWarpsPerBlock * 32, MINB) spmm_flat_kernel(co
                 if (act[v]) {
                     if (p.stream_y) acc[v].store_streaming(ybase[v] + (uint64_t)(uint32_t)row * ldy_bytes);
                     else acc[v].store(ybase[v] + (uint64_t)(uint32_t)row * ldy_bytes);
+                    if (p.red_agg && !red_skip_first) red_row_slice<VEC>(p, (uint32_t)row, cofs_v[v], acc[v]);
                 }
+            red_skip_first = false;
         }
         ++row;
         if constexpr (!FLAG) {
@@ -312,7 +330,12 @@ __global__ void __launch_bounds__(kWarpsPerBlock * 32, MINB) spmm_flat_kernel(co
                             sum[v].add(part);
                         }
                     }
-                    emit_row<VEC, VPL, 32>(p, out_row, sum, act, cofs_v, kFull);
+                    RowPrefetch<VEC, VPL> pf2;
+                    prefetch_row<VEC, VPL>(p, out_row, act, cofs_v, pf2);
+                    AccPack<VEC, VPL> pack;
+#pragma unroll
+                    for (int v = 0; v < VPL; ++v) pack.s[v] = sum[v];
+                    emit_row_call<VEC, VPL, 32>(&p, out_row, pack, cofs_v[0], kFull, pf2.row_scale, pf2.z_scale, pf2.self_coef);
                 } else {
 #pragma unroll
                     for (int v = 0; v < VPL; ++v) {
@@ -328,6 +351,7 @@ __global__ void __launch_bounds__(kWarpsPerBlock * 32, MINB) spmm_flat_kernel(co
                         part.load_l2(yp);          // the finishing tile's partial
                         part.add(sum);             // Y = finisher + (c0 + c1 + ...): the order of the separate fold kernel
                         part.store(yp);
+                        if (p.red_agg) red_row_slice<VEC>(p, out_row, cofs_v[v], part);
                     }
                 }
                 if (lane == 0) p.run_count[run] = 0u;  // ready for the next hop
@@ -595,6 +619,7 @@ static cudaError_t launch_flat(const SpmmParams &p, bool accum, dim3 grid, cudaS
 {
     const int32_t *tags = accum ? nullptr : g_flat_tags;
     if (!accum && p.epi.active) {
+        // the fused flush keeps the next row's aggregate / scales in registers from the row start on: two CTAs per SM
         if (tags) spmm_flat_kernel<VEC, VPL, U, false, (MINB > 3 ? 3 : MINB), 1, false, true, true><<<grid, kWarpsPerBlock * 32, 0, stream>>>(p, tags);
         else spmm_flat_kernel<VEC, VPL, U, false, (MINB > 3 ? 3 : MINB), 1, false, true><<<grid, kWarpsPerBlock * 32, 0, stream>>>(p, nullptr);
         return cudaGetLastError();
@@ -719,7 +744,7 @@ int spmm_launch_ex(sglb200_graph *g, const float *X, int64_t ldx, float *Y, int6
     auto all_fit = [&](int v) {
         bool ok = d % v == 0 && fits(ldx, X, v) && fits(ldy, Y, v);
         if (epi) ok = ok && fits(epi->ldz, epi->Z, v) && fits(epi->ld_agg, epi->agg, v) && fits(epi->ld_self, epi->self_x, v) &&
-                  fits(epi->ldx0, epi->x0, v);
+                  fits(epi->ldx0, epi->x0, v) && fits(epi->ld_add, epi->add_rows, v);
         return ok;
     };
     if (!all_fit(4)) max_vec = 2;
@@ -736,7 +761,9 @@ int spmm_launch_ex(sglb200_graph *g, const float *X, int64_t ldx, float *Y, int6
 
     // TMA-staged kernel (spmm_tma.cu): float4 rows of 64..256 floats on graphs without empty rows
     bool use_tma = false;
-    if (!accumulate && !use_groups && max_vec == 4 && d > 64 && d <= 128 && spmm_variant() < 10 && env_int("SGLB200_TMA", 0) != 0) {
+    const bool lean_sum = epi && (epi->agg_op == EPI_AGG_SUM || epi->agg_op == EPI_AGG_WEIGHTED) && !epi->agg_init && !epi->row_scale &&
+                          !epi->Z && epi->acc_scale == 0.0f;   // handled by the warp / lane-group kernels' lean flush
+    if (!accumulate && !lean_sum && !use_groups && max_vec == 4 && d > 64 && d <= 128 && spmm_variant() < 10 && env_int("SGLB200_TMA", 0) != 0) {
         if (g->empty_rows < 0) {
             const int st = build_stream_tags(g, stream);
             if (st != SGLB200_OK) return st;
@@ -796,8 +823,19 @@ int spmm_launch_ex(sglb200_graph *g, const float *X, int64_t ldx, float *Y, int6
         if (epi) {
             SGL_REQUIRE(s->n_runs == 0 || p.fold, "spmm: the fused row flush needs the in-kernel fold (d <= 512)");
             SGL_REQUIRE(col_blocks == 1, "spmm: the fused row flush supports feature widths up to 512");
-            p.epi = *epi;
-            p.epi.active = 1;
+            const bool only_running_sum = (epi->agg_op == EPI_AGG_SUM || epi->agg_op == EPI_AGG_WEIGHTED) && !epi->agg_init &&
+                                          epi->agg_div == 0.0f && !epi->row_scale && !epi->self_coef && !epi->Z &&
+                                          epi->acc_scale == 0.0f && Y != nullptr;
+            if (only_running_sum) {
+                // nothing but a running sum: the lean flush adds the row to the aggregate with one L2 reduction
+                p.red_agg = epi->agg;
+                p.ld_red = epi->ld_agg;
+                p.red_w = epi->agg_w;
+                p.red_weighted = epi->agg_op == EPI_AGG_WEIGHTED;
+            } else {
+                p.epi = *epi;
+                p.epi.active = 1;
+            }
         }
         p.tail_run = s->tail_run;
         p.head_run = s->head_run;
@@ -833,7 +871,9 @@ int spmm_launch_ex(sglb200_graph *g, const float *X, int64_t ldx, float *Y, int6
         }
         if (g->empty_rows == 0 && g->n_cols < (1LL << 30)) tags = g->idx_tag;
     }
-    g_flat_tags = tags;
+    // the warp kernel keeps its row-pointer windows by default: its check-free groups beat the per-non-zero flag test
+    // (measured: arxiv 101 vs 111 us, products 5.3 vs 6.0 ms per hop); the lane-group and TMA kernels use the flags
+    g_flat_tags = env_int("SGLB200_FLAT_FLAGS", 0) != 0 ? tags : nullptr;
     cudaError_t e = cudaSuccess;
 #define SGL_SHAPE(V, L, UU, MB) \
     if (vec == V && vpl == L) e = launch_flat<V, L, UU, MB>(p, acc, grid, stream)

@@ -24,6 +24,12 @@ struct Epilogue {
     const float *self_coef;
     const float *self_x;
     int64_t ld_self;
+    // label propagation (tricks/utils.py:54-56):  y = clamp(acc_scale * y + add_rows[i, :], lo, hi); acc_scale == 0: unused
+    float acc_scale;
+    const float *add_rows;
+    int64_t ld_add;
+    int clamp;
+    float clamp_lo, clamp_hi;
     float *Z;
     int64_t ldz;
     const float *z_scale;
@@ -72,6 +78,12 @@ struct SpmmParams {
     const int64_t *run_base;
     const int32_t *run_len;
     unsigned int *run_count;
+    // running sum / mean / weighted aggregate on the plain (lean) row flush: every finished row is also added to
+    // red_agg[row, :] (scaled by red_w when red_weighted) with one fire-and-forget L2 reduction; NULL: off
+    float *red_agg;
+    int64_t ld_red;
+    float red_w;
+    int red_weighted;
     Epilogue epi;
 };
 
@@ -223,30 +235,78 @@ __device__ __forceinline__ float epi_nan_min(float a, float b) { return (a < b |
 //   max / min  NaN-propagating running extremum                                       (max_message_op.py:11-12)
 //   osd        c_k = <x, y_k> / (|y_k| + 1e-10) / (|x| + 1e-10), softmax over hops, weighted sum (over_smooth_distance_op.py:11-33);
 //              |c_k| <= 1, so the softmax needs no max shift and folds into one pass: num += e^{c_k} y_k, den += e^{c_k}
+// The per-row SCALARS of the fused row flush (degree scales, teleport coefficient), fetched when the row STARTS so that
+// their latency hides behind the row's gathers: a load issued inside the flush stalls the warp once per row (arxiv-shape
+// tiles hold ~128 one-entry rows).  Row-sized reads (running max / min, over-smoothing distance, teleport row) stay in the
+// flush: they are the slow path; sum / mean / weighted aggregates need no read at all (red.global.add below).
+template <int VEC, int VPL> struct RowPrefetch {
+    float row_scale, z_scale, self_coef;
+};
+
+template <int VEC, int VPL>
+__device__ __forceinline__ void prefetch_row(const SpmmParams &p, uint32_t row, const bool (&act)[VPL], const int (&cofs)[VPL],
+                                             RowPrefetch<VEC, VPL> &pf)
+{
+    const Epilogue &e = p.epi;
+    pf.row_scale = e.row_scale ? __ldg(e.row_scale + row) : 1.0f;
+    pf.z_scale = (e.Z && e.z_scale) ? __ldg(e.z_scale + row) : 1.0f;
+    pf.self_coef = e.self_coef ? __ldg(e.self_coef + row) : 0.0f;
+    (void)act;
+    (void)cofs;
+}
+
+// agg[0..VEC) += v[0..VEC) as ONE fire-and-forget reduction at the L2 (REDG.E.ADD.F32x4): no load, no stall.  Each element
+// receives exactly one IEEE add per hop and the hops are ordered by kernel boundaries, so the running sum equals the
+// reference's left-to-right sum bit for bit (the hardware flushes SUBNORMAL sums to zero; normal-range values are exact).
+template <int VEC> __device__ __forceinline__ void red_add(float *p, const float (&v)[VEC])
+{
+    if constexpr (VEC == 4)
+        asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(p), "f"(v[0]), "f"(v[1]), "f"(v[2]), "f"(v[3]) : "memory");
+    else if constexpr (VEC == 2)
+        asm volatile("red.global.add.v2.f32 [%0], {%1, %2};" ::"l"(p), "f"(v[0]), "f"(v[1]) : "memory");
+    else
+        asm volatile("red.global.add.f32 [%0], %1;" ::"l"(p), "f"(v[0]) : "memory");
+}
+
 template <int VEC, int VPL, int GW>
 __device__ __forceinline__ void emit_row(const SpmmParams &p, uint32_t row, const Slice<VEC> (&acc)[VPL],
-                                         const bool (&act)[VPL], const int (&cofs)[VPL], unsigned gmask)
+                                         const bool (&act)[VPL], const int (&cofs)[VPL], unsigned gmask,
+                                         const RowPrefetch<VEC, VPL> &pf)
 {
     const Epilogue &e = p.epi;
     float y[VPL][VEC];
 #pragma unroll
     for (int v = 0; v < VPL; ++v) acc[v].unpack(y[v]);
     if (e.row_scale) {
-        const float s = __ldg(e.row_scale + row);
 #pragma unroll
         for (int v = 0; v < VPL; ++v)
 #pragma unroll
-            for (int q = 0; q < VEC; ++q) y[v][q] = __fmul_rn(y[v][q], s);
+            for (int q = 0; q < VEC; ++q) y[v][q] = __fmul_rn(y[v][q], pf.row_scale);
     }
     if (e.self_coef) {
-        const float c = __ldg(e.self_coef + row);
 #pragma unroll
         for (int v = 0; v < VPL; ++v)
             if (act[v]) {
                 float x[VEC];
                 load_plain<VEC>(x, e.self_x + (size_t)row * e.ld_self + cofs[v]);
 #pragma unroll
-                for (int q = 0; q < VEC; ++q) y[v][q] = fmaf(c, x[q], y[v][q]);
+                for (int q = 0; q < VEC; ++q) y[v][q] = fmaf(pf.self_coef, x[q], y[v][q]);
+            }
+    }
+    if (e.acc_scale != 0.0f) {
+#pragma unroll
+        for (int v = 0; v < VPL; ++v)
+            if (act[v]) {
+                float r[VEC];
+#pragma unroll
+                for (int q = 0; q < VEC; ++q) r[q] = 0.0f;
+                if (e.add_rows) load_plain<VEC>(r, e.add_rows + (size_t)row * e.ld_add + cofs[v]);
+#pragma unroll
+                for (int q = 0; q < VEC; ++q) {
+                    float t = __fadd_rn(__fmul_rn(e.acc_scale, y[v][q]), r[q]);   // alpha * (A^ out) + res, separately rounded
+                    if (e.clamp) t = fminf(fmaxf(t, e.clamp_lo), e.clamp_hi);
+                    y[v][q] = t;
+                }
             }
     }
     if (p.Y) {
@@ -261,17 +321,27 @@ __device__ __forceinline__ void emit_row(const SpmmParams &p, uint32_t row, cons
             }
     }
     if (e.Z) {
-        const float zs = e.z_scale ? __ldg(e.z_scale + row) : 1.0f;
 #pragma unroll
         for (int v = 0; v < VPL; ++v)
             if (act[v]) {
                 float z[VEC];
 #pragma unroll
-                for (int q = 0; q < VEC; ++q) z[q] = __fmul_rn(y[v][q], zs);
+                for (int q = 0; q < VEC; ++q) z[q] = __fmul_rn(y[v][q], pf.z_scale);
                 store_slice<VEC>(e.Z + (size_t)row * e.ldz + cofs[v], z);
             }
     }
     if (e.agg_op == EPI_AGG_NONE) return;
+    if ((e.agg_op == EPI_AGG_SUM || e.agg_op == EPI_AGG_WEIGHTED) && !e.agg_init && e.agg_div == 0.0f) {
+#pragma unroll
+        for (int v = 0; v < VPL; ++v)
+            if (act[v]) {
+                float t[VEC];
+#pragma unroll
+                for (int q = 0; q < VEC; ++q) t[q] = e.agg_op == EPI_AGG_SUM ? y[v][q] : __fmul_rn(y[v][q], e.agg_w);
+                red_add<VEC>(e.agg + (size_t)row * e.ld_agg + cofs[v], t);
+            }
+        return;
+    }
     float wk = 1.0f;   // osd: e^{c_k}
     if (e.agg_op == EPI_AGG_OSD) {
         float dot = 0.0f, ny = 0.0f;
@@ -293,36 +363,32 @@ __device__ __forceinline__ void emit_row(const SpmmParams &p, uint32_t row, cons
         }
         const float c = __fdiv_rn(__fdiv_rn(dot, sqrtf(ny) + 1e-10f), __ldg(e.x0_norm + row));
         wk = expf(c);
-        float den = wk;
-        if (!e.agg_init) den += e.den[row];
-        if (e.osd_final) wk = __fdiv_rn(wk, den);   // applied below together with the division of the numerator
-        else if ((threadIdx.x & (GW - 1)) == 0) e.den[row] = den;
+        const float den = wk + (e.agg_init ? 0.0f : e.den[row]);
         if (e.osd_final) {
             // out = (num + e^{c} y) / den, evaluated as num/den + (e^{c}/den) y
+            wk = __fdiv_rn(wk, den);
 #pragma unroll
             for (int v = 0; v < VPL; ++v)
                 if (act[v]) {
-                    float *ap = e.agg + (size_t)row * e.ld_agg + cofs[v];
                     float a[VEC];
-                    if (e.agg_init) {
 #pragma unroll
-                        for (int q = 0; q < VEC; ++q) a[q] = 0.0f;
-                    } else {
-                        load_plain<VEC>(a, ap);
-                    }
+                    for (int q = 0; q < VEC; ++q) a[q] = 0.0f;
+                    if (!e.agg_init) load_plain<VEC>(a, e.agg + (size_t)row * e.ld_agg + cofs[v]);
 #pragma unroll
-                    for (int q = 0; q < VEC; ++q) a[q] = fmaf(wk, y[v][q], __fdiv_rn(a[q], den));
-                    store_slice<VEC>(ap, a);
+                    for (int q = 0; q < VEC; ++q) a[q] = fmaf(wk, y[v][q], e.agg_init ? 0.0f : __fdiv_rn(a[q], den));
+                    store_slice<VEC>(e.agg + (size_t)row * e.ld_agg + cofs[v], a);
                 }
             return;
         }
+        if ((threadIdx.x & (GW - 1)) == 0) e.den[row] = den;
     }
 #pragma unroll
     for (int v = 0; v < VPL; ++v)
         if (act[v]) {
-            float *ap = e.agg + (size_t)row * e.ld_agg + cofs[v];
             float a[VEC];
-            if (!e.agg_init) load_plain<VEC>(a, ap);
+#pragma unroll
+            for (int q = 0; q < VEC; ++q) a[q] = 0.0f;
+            if (!e.agg_init) load_plain<VEC>(a, e.agg + (size_t)row * e.ld_agg + cofs[v]);
 #pragma unroll
             for (int q = 0; q < VEC; ++q) {
                 const float yv = y[v][q];
@@ -337,8 +403,45 @@ __device__ __forceinline__ void emit_row(const SpmmParams &p, uint32_t row, cons
                 if (e.agg_div != 0.0f) r = __fdiv_rn(r, e.agg_div);
                 a[q] = r;
             }
-            store_slice<VEC>(ap, a);
+            store_slice<VEC>(e.agg + (size_t)row * e.ld_agg + cofs[v], a);
         }
+}
+
+// the lean flush's aggregate update: red_agg[row, cofs ..] += (weighted ? acc * w : acc)
+template <int VEC> __device__ __forceinline__ void red_row_slice(const SpmmParams &p, uint32_t row, int cofs, const Slice<VEC> &acc)
+{
+    float t[VEC];
+    acc.unpack(t);
+    if (p.red_weighted) {
+#pragma unroll
+        for (int q = 0; q < VEC; ++q) t[q] = __fmul_rn(t[q], p.red_w);
+    }
+    red_add<VEC>(p.red_agg + (size_t)row * p.ld_red + cofs, t);
+}
+
+// Out-of-line entry of the fused row flush.  emit_row inlined at every row-end site of the unrolled walk (8-16 sites per
+// kernel) blows the hop kernels up to ~140 KB of SASS and the instruction cache thrashes (measured: +55 % per hop on
+// products-shape whatever the epilogue does); ONE copy per kernel, reached by a call, costs ~20 instructions per row.
+// cofs0 = first column of this lane's first slice; slice v starts GW * VEC columns further.
+template <int VEC, int VPL> struct AccPack {
+    Slice<VEC> s[VPL];
+};
+template <int VEC, int VPL, int GW>
+__device__ __noinline__ void emit_row_call(const SpmmParams *pp, uint32_t row, AccPack<VEC, VPL> acc, int cofs0, unsigned gmask,
+                                           float row_scale, float z_scale, float self_coef)
+{
+    bool act[VPL];
+    int cofs[VPL];
+#pragma unroll
+    for (int v = 0; v < VPL; ++v) {
+        cofs[v] = cofs0 + v * GW * VEC;
+        act[v] = cofs[v] < pp->d;
+    }
+    RowPrefetch<VEC, VPL> pf;
+    pf.row_scale = row_scale;
+    pf.z_scale = z_scale;
+    pf.self_coef = self_coef;
+    emit_row<VEC, VPL, GW>(*pp, row, acc.s, act, cofs, gmask, pf);
 }
 
 }  // namespace sglb200

@@ -18,16 +18,19 @@ namespace sglb200 {
 // FLAG: the column stream is the tagged one (bit 31 = last non-zero of its row; graphs without empty rows): a row ends
 // where the stream says so, which turns the group-divergent row flush (window refill + shuffles) into a few predicated
 // instructions -- with 8 groups per warp the divergent flush was 70 % of the instruction stream.
-template <int G, int U, bool ACCUM, bool EPI = false, bool FLAG = false>
-__global__ void __launch_bounds__(kWarpsPerBlock * 32, G == 4 ? 2 : 3) spmm_group_kernel(const SpmmParams p, const int32_t *__restrict__ idx_tag)
+template <int G, int U, bool ACCUM, bool EPI = false, bool FLAG = false, int MINB = 3>
+__global__ void __launch_bounds__(kWarpsPerBlock * 32, MINB) spmm_group_kernel(const __grid_constant__ SpmmParams p, const int32_t *__restrict__ idx_tag)
 {
     static_assert(!(FLAG && ACCUM), "the flagged walk starts every chain from zero");
     static_assert(!(EPI && ACCUM), "the fused row flush starts every chain from zero");
-    constexpr int NG = 32 / G;   // tiles per warp
-    constexpr int R = 32 / G;    // (col, val) pairs each lane fetches per batch of 32
+    constexpr int NG = 32 / G;             // tiles per warp
+    constexpr int BATCH = G == 4 ? 16 : 32;  // (col, val) pairs published per step (two batches live per group)
+    constexpr int R = BATCH / G;           // pairs each lane fetches per batch
+    constexpr int PSTRIDE = 2 * BATCH + 2; // int2 per group: +2 staggers the groups over the banks (the 32/G groups read
+                                           // the same position of their own buffers in one LDS.64)
     static_assert(G == 4 || G == 8 || G == 16, "group width");
-    static_assert(32 % U == 0, "U must divide the batch of 32 non-zeros");
-    __shared__ int2 s_pairs[kWarpsPerBlock][NG][64];
+    static_assert(BATCH % U == 0, "U must divide the batch");
+    __shared__ int2 s_pairs[kWarpsPerBlock][NG][PSTRIDE];
     const int lane = threadIdx.x & 31;
     const int gl = lane & (G - 1);   // lane inside the group
     const int gid = lane / G;        // group inside the warp
@@ -52,6 +55,10 @@ __global__ void __launch_bounds__(kWarpsPerBlock * 32, G == 4 ? 2 : 3) spmm_grou
     Slice<4> &acc = accs[0];
     const bool acts[1] = {act};
     const int cofss[1] = {cofs};
+    bool red_skip_first = false;   // lean flush + running aggregate: see spmm_flat_kernel
+    if constexpr (!EPI) {
+        if (p.red_agg && p.fold) red_skip_first = p.head_run[t] >= 0;
+    }
     int cont_slot = -1;   // fused row flush: see spmm_flat_kernel
     if constexpr (EPI) {
         if (p.fold) {
@@ -60,10 +67,14 @@ __global__ void __launch_bounds__(kWarpsPerBlock * 32, G == 4 ? 2 : 3) spmm_grou
         }
     }
 
+    RowPrefetch<4, 1> pf;
     auto init_acc = [&](int r) {
         acc.zero();
         if (ACCUM) {
             if (act && r < n_rows) acc.load(ybase + (uint64_t)(uint32_t)r * ldy_bytes);
+        }
+        if constexpr (EPI) {
+            if (r < n_rows) prefetch_row<4, 1>(p, (uint32_t)r, acts, cofss, pf);
         }
     };
     // ends (relative to j0) of rows row_base .. row_base+G-1, one per lane of the group
@@ -82,6 +93,9 @@ __global__ void __launch_bounds__(kWarpsPerBlock * 32, G == 4 ? 2 : 3) spmm_grou
         init_acc(starts_here ? row : n_rows);
     } else {
         init_acc(n_rows);
+        if constexpr (EPI) {
+            if (row < n_rows) prefetch_row<4, 1>(p, (uint32_t)row, acts, cofss, pf);   // init_acc(n_rows) fetched nothing
+        }
     }
     auto flush_row = [&]() {
         if constexpr (EPI) {
@@ -89,11 +103,17 @@ __global__ void __launch_bounds__(kWarpsPerBlock * 32, G == 4 ? 2 : 3) spmm_grou
                 if (act) acc.store(reinterpret_cast<char *>(p.carry_ws + (int64_t)cont_slot * p.ws_ld) + (size_t)cofs * sizeof(float));
                 cont_slot = -1;
             } else {
-                emit_row<4, 1, G>(p, (uint32_t)row, accs, acts, cofss, gmask);
+                AccPack<4, 1> pack;
+                pack.s[0] = acc;
+                emit_row_call<4, 1, G>(&p, (uint32_t)row, pack, cofs, gmask, pf.row_scale, pf.z_scale, pf.self_coef);
             }
-        } else if (act) {
-            if (p.stream_y) acc.store_streaming(ybase + (uint64_t)(uint32_t)row * ldy_bytes);
-            else acc.store(ybase + (uint64_t)(uint32_t)row * ldy_bytes);
+        } else {
+            if (act) {
+                if (p.stream_y) acc.store_streaming(ybase + (uint64_t)(uint32_t)row * ldy_bytes);
+                else acc.store(ybase + (uint64_t)(uint32_t)row * ldy_bytes);
+                if (p.red_agg && !red_skip_first) red_row_slice<4>(p, (uint32_t)row, cofs, acc);
+            }
+            red_skip_first = false;
         }
         ++row;
         if constexpr (!FLAG) {
@@ -121,7 +141,7 @@ __global__ void __launch_bounds__(kWarpsPerBlock * 32, G == 4 ? 2 : 3) spmm_grou
     auto fetch_batch = [&](int b) {
 #pragma unroll
         for (int i = 0; i < R; ++i) {
-            const int nb = b * 32 + i * G + gl;
+            const int nb = b * BATCH + i * G + gl;
             col_next[i] = 0;
             val_next[i] = 0.0f;
             if (nb < n_nnz) {
@@ -134,7 +154,7 @@ __global__ void __launch_bounds__(kWarpsPerBlock * 32, G == 4 ? 2 : 3) spmm_grou
     auto publish_batch = [&](int b) {
         __syncwarp(gmask);  // the group is done with the batch that used this buffer two batches ago
 #pragma unroll
-        for (int i = 0; i < R; ++i) pairs[(b & 1) * 32 + i * G + gl] = make_int2(col_next[i], __float_as_int(val_next[i]));
+        for (int i = 0; i < R; ++i) pairs[(b & 1) * BATCH + i * G + gl] = make_int2(col_next[i], __float_as_int(val_next[i]));
         __syncwarp(gmask);
         fetch_batch(b + 1);
     };
@@ -143,8 +163,8 @@ __global__ void __launch_bounds__(kWarpsPerBlock * 32, G == 4 ? 2 : 3) spmm_grou
 #pragma unroll 1
     for (int g = 0; g < n_groups; ++g) {
         const int pos = g * U;
-        if ((pos & 31) == 0) publish_batch(pos >> 5);
-        const int2 *pp = pairs + (pos & 63);
+        if (pos % BATCH == 0) publish_batch(pos / BATCH);
+        const int2 *pp = pairs + (pos % (2 * BATCH));
         Slice<4> buf[U];
 #pragma unroll
         for (int u = 0; u < U; ++u) buf[u].load_nc(xbase + (uint64_t)((uint32_t)pp[u].x & (FLAG ? 0x3fffffffu : 0xffffffffu)) * ldx_bytes);
@@ -207,7 +227,11 @@ __global__ void __launch_bounds__(kWarpsPerBlock * 32, G == 4 ? 2 : 3) spmm_grou
                             sums[0].add(part);
                         }
                     }
-                    emit_row<4, 1, G>(p, (uint32_t)p.run_row[run], sums, acts, cofss, gmask);
+                    RowPrefetch<4, 1> pf2;
+                    prefetch_row<4, 1>(p, (uint32_t)p.run_row[run], acts, cofss, pf2);
+                    AccPack<4, 1> pack;
+                    pack.s[0] = sums[0];
+                    emit_row_call<4, 1, G>(&p, (uint32_t)p.run_row[run], pack, cofs, gmask, pf2.row_scale, pf2.z_scale, pf2.self_coef);
                 } else if (act) {
                     const char *ws0 = reinterpret_cast<const char *>(p.carry_ws + p.run_base[run] * p.ws_ld);
                     const size_t ws_ld_bytes = (size_t)p.ws_ld * sizeof(float);
@@ -222,6 +246,7 @@ __global__ void __launch_bounds__(kWarpsPerBlock * 32, G == 4 ? 2 : 3) spmm_grou
                     part.load_l2(yp);
                     part.add(sum);
                     part.store(yp);
+                    if (p.red_agg) red_row_slice<4>(p, (uint32_t)p.run_row[run], cofs, part);
                 }
                 if (gl == 0) p.run_count[run] = 0u;
             }
@@ -238,6 +263,7 @@ static cudaError_t launch_group(const SpmmParams &p, bool accum, const int32_t *
     if (accum) spmm_group_kernel<G, U, true><<<blocks, kWarpsPerBlock * 32, 0, stream>>>(p, nullptr);
     else if (p.epi.active && idx_tag) spmm_group_kernel<G, U, false, true, true><<<blocks, kWarpsPerBlock * 32, 0, stream>>>(p, idx_tag);
     else if (p.epi.active) spmm_group_kernel<G, U, false, true><<<blocks, kWarpsPerBlock * 32, 0, stream>>>(p, nullptr);
+    else if (idx_tag && U == 4) spmm_group_kernel<G, U, false, false, true, 4><<<blocks, kWarpsPerBlock * 32, 0, stream>>>(p, idx_tag);
     else if (idx_tag) spmm_group_kernel<G, U, false, false, true><<<blocks, kWarpsPerBlock * 32, 0, stream>>>(p, idx_tag);
     else spmm_group_kernel<G, U, false><<<blocks, kWarpsPerBlock * 32, 0, stream>>>(p, nullptr);
     return cudaGetLastError();
@@ -248,9 +274,11 @@ static cudaError_t launch_group(const SpmmParams &p, bool accum, const int32_t *
 cudaError_t spmm_group_launch(const SpmmParams &p, bool accum, const int32_t *idx_tag, cudaStream_t stream)
 {
     const int slices = (p.d + 3) / 4;
-    if (slices <= 4) return launch_group<4, 8>(p, accum, idx_tag, stream);
-    if (slices <= 8) return launch_group<8, 8>(p, accum, idx_tag, stream);
-    return launch_group<16, 8>(p, accum, idx_tag, stream);
+    static const char *u_env = getenv("SGLB200_GROUP_U");
+    const bool u4 = u_env && atoi(u_env) == 4 && !accum && !p.epi.active && idx_tag;   // experiment: 4 rows in flight, 32 warps / SM
+    if (slices <= 4) return u4 ? launch_group<4, 4>(p, accum, idx_tag, stream) : launch_group<4, 8>(p, accum, idx_tag, stream);
+    if (slices <= 8) return u4 ? launch_group<8, 4>(p, accum, idx_tag, stream) : launch_group<8, 8>(p, accum, idx_tag, stream);
+    return u4 ? launch_group<16, 4>(p, accum, idx_tag, stream) : launch_group<16, 8>(p, accum, idx_tag, stream);
 }
 
 }  // namespace sglb200

@@ -64,7 +64,7 @@ __device__ __forceinline__ void gather4(uint32_t dst, const CUtensorMap *map, ui
 
 // smem per warp: [ring: stages x 2 blocks x blk_bytes][cols: 2 x 64 u32][vals: 2 x 64 f32][4 mbarriers]
 template <bool EPI, bool UNITW>
-__global__ void __launch_bounds__(kWarpsPerBlock * 32) spmm_tma_kernel(const __grid_constant__ CUtensorMap xmap, const SpmmParams p,
+__global__ void __launch_bounds__(kWarpsPerBlock * 32) spmm_tma_kernel(const __grid_constant__ CUtensorMap xmap, const __grid_constant__ SpmmParams p,
                                                                        const uint32_t *__restrict__ idx_tag, int blk_bytes,
                                                                        int warp_bytes, int64_t total_warps)
 {
@@ -115,6 +115,10 @@ __global__ void __launch_bounds__(kWarpsPerBlock * 32) spmm_tma_kernel(const __g
         }
         Slice<4> acc[1];
         acc[0].zero();
+        RowPrefetch<4, 1> pf;
+        if constexpr (EPI) {
+            if (row < n_rows) prefetch_row<4, 1>(p, (uint32_t)row, act1, cofs1, pf);
+        }
 
         auto load_chunk = [&](int c) {   // lane 0 only
             const uint32_t b = (uint32_t)(c & 1);
@@ -140,7 +144,9 @@ __global__ void __launch_bounds__(kWarpsPerBlock * 32) spmm_tma_kernel(const __g
                     if (act1[0]) acc[0].store(reinterpret_cast<char *>(p.carry_ws + (int64_t)cont_slot * p.ws_ld) + lane * 16);
                     cont_slot = -1;
                 } else {
-                    emit_row<4, 1, 32>(p, (uint32_t)row, acc, act1, cofs1, kFull);
+                    AccPack<4, 1> pack;
+                    pack.s[0] = acc[0];
+                    emit_row_call<4, 1, 32>(&p, (uint32_t)row, pack, cofs1[0], kFull, pf.row_scale, pf.z_scale, pf.self_coef);
                 }
             } else if (act1[0]) {
                 char *yp = reinterpret_cast<char *>(p.Y + (size_t)row * p.ldy) + lane * 16;
@@ -149,6 +155,9 @@ __global__ void __launch_bounds__(kWarpsPerBlock * 32) spmm_tma_kernel(const __g
             }
             ++row;
             acc[0].zero();
+            if constexpr (EPI) {
+                if (row < n_rows) prefetch_row<4, 1>(p, (uint32_t)row, act1, cofs1, pf);
+            }
         };
 
         // the one row a flag cannot retire: a cut row whose non-zeros all lie in earlier tiles (the boundary fell between
@@ -251,7 +260,11 @@ __global__ void __launch_bounds__(kWarpsPerBlock * 32) spmm_tma_kernel(const __g
                                 sum[0].add(part);
                             }
                         }
-                        emit_row<4, 1, 32>(p, out_row, sum, act1, cofs1, kFull);
+                        RowPrefetch<4, 1> pf2;
+                        prefetch_row<4, 1>(p, out_row, act1, cofs1, pf2);
+                        AccPack<4, 1> pack;
+                        pack.s[0] = sum[0];
+                        emit_row_call<4, 1, 32>(&p, out_row, pack, cofs1[0], kFull, pf2.row_scale, pf2.z_scale, pf2.self_coef);
                     } else if (act1[0]) {
                         sum[0].load_l2(ws0);
                         for (int u = 1; u < n_carriers; ++u) {

@@ -637,6 +637,34 @@ class FeatureSplitOperator:
         dist.all_gather(parts, padded, group=self.group)
         return torch.cat([parts[q][:, :int(bounds[q + 1] - bounds[q])] for q in range(self.world)], dim=1)
 
+    def rows_from_columns(self, block: torch.Tensor, d: int) -> torch.Tensor:
+        """The one real exchange of the feature split: turn this rank's column block of a hop ([N, d_p]) into its ROW shard
+        with all d columns ([N_p, d], rows [row_bounds[p], row_bounds[p+1])) -- the layout a data-parallel head trains on
+        (reference tasks/node_classification_dist.py:73-85 shards the node ids over ranks).  One all_to_all_single moving
+        N*d*4/world bytes per rank (an all-gather of the blocks would move world times more)."""
+        if self.world == 1:
+            return block
+        n = int(block.shape[0])
+        cb = self.column_bounds(d, self.world)
+        rb = self.row_bounds(n, self.world)
+        widths = [int(cb[q + 1] - cb[q]) for q in range(self.world)]
+        rows = [int(rb[q + 1] - rb[q]) for q in range(self.world)]
+        mine_w, mine_r = widths[self.rank], rows[self.rank]
+        send = block.contiguous().reshape(-1)
+        recv = torch.empty(mine_r * d, dtype=block.dtype, device=block.device)
+        dist.all_to_all_single(recv, send, output_split_sizes=[mine_r * w for w in widths],
+                               input_split_sizes=[r * mine_w for r in rows], group=self.group)
+        out = torch.empty((mine_r, d), dtype=block.dtype, device=block.device)
+        off = 0
+        for q in range(self.world):
+            out[:, int(cb[q]):int(cb[q + 1])] = recv[off:off + mine_r * widths[q]].view(mine_r, widths[q])
+            off += mine_r * widths[q]
+        return out
+
+    @staticmethod
+    def row_bounds(n: int, world: int) -> np.ndarray:
+        return np.asarray([(n * p) // world for p in range(world + 1)], dtype=np.int64)
+
     def close(self):
         if self._op is not None:
             self._op.close()

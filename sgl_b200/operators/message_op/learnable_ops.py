@@ -133,6 +133,79 @@ class LearnableWeightedMessageOp(MessageOp):
         return two_dim_weighted_add(sel, weight_list=weights)
 
 
+class _FusedIterate(torch.autograd.Function):
+    """The recursive gated combination of IterateLearnableWeightedMessageOp, forward and backward in libsglb200
+    (sglb200_it_forward / sglb200_it_backward, csrc/iterate.cu): 2 K' dot products per node replace the K' hstacks of
+    [B, 2d] and the O(K'^2) [B, d] products of the torch expression."""
+
+    @staticmethod
+    def forward(ctx, weight, bias, *feats):
+        lib = _lib.load()
+        feats = [f.detach().float().contiguous() for f in feats]
+        B, d = int(feats[0].shape[0]), int(feats[0].shape[1])
+        kp, dev = len(feats), feats[0].device
+        w = weight.detach().reshape(-1).float().contiguous()
+        b = bias.detach().reshape(-1).float().contiguous()
+        dots = torch.empty((B, 2 * kp), dtype=torch.float32, device=dev)
+        hop_w = torch.empty((B, kp), dtype=torch.float32, device=dev)
+        out = torch.empty((B, d), dtype=torch.float32, device=dev)
+        with torch.cuda.device(dev):
+            stream = c_void_p(torch.cuda.current_stream().cuda_stream)
+            _lib.check(lib.sglb200_it_forward(_lib.ptr_array([f.data_ptr() for f in feats]), kp, B, d, c_void_p(w.data_ptr()),
+                                              c_void_p(b.data_ptr()), c_void_p(dots.data_ptr()), c_void_p(hop_w.data_ptr()),
+                                              c_void_p(out.data_ptr()), stream), "it_forward")
+        ctx.meta = (weight.shape, bias.shape)
+        ctx.save_for_backward(w, b, dots, *feats)
+        return out
+
+    @staticmethod
+    def backward(ctx, grad_out):
+        lib = _lib.load()
+        w_shape, b_shape = ctx.meta
+        w, b, dots, *feats = ctx.saved_tensors
+        B, d = int(feats[0].shape[0]), int(feats[0].shape[1])
+        dev = feats[0].device
+        grad_out = grad_out.contiguous().float()
+        grads = [torch.zeros_like(f) for f in feats]
+        gw, gb = torch.zeros_like(w), torch.zeros_like(b)
+        with torch.cuda.device(dev):
+            stream = c_void_p(torch.cuda.current_stream().cuda_stream)
+            _lib.check(lib.sglb200_it_backward(_lib.ptr_array([f.data_ptr() for f in feats]), len(feats), B, d,
+                                               c_void_p(w.data_ptr()), c_void_p(b.data_ptr()), c_void_p(dots.data_ptr()),
+                                               c_void_p(grad_out.data_ptr()), _lib.ptr_array([g.data_ptr() for g in grads]),
+                                               c_void_p(gw.data_ptr()), c_void_p(gb.data_ptr()), stream), "it_backward")
+        return (gw.view(w_shape), gb.view(b_shape), *grads)
+
+
+class _FusedReluConcat(torch.autograd.Function):
+    """hstack(y_0, relu(y_1), ..., relu(y_{K'-1})) in one pass (sglb200_relu_concat), gradient masked on the way back."""
+
+    @staticmethod
+    def forward(ctx, *ys):
+        lib = _lib.load()
+        ys = [y.detach().float().contiguous() for y in ys]
+        B, h = int(ys[0].shape[0]), int(ys[0].shape[1])
+        out = torch.empty((B, len(ys) * h), dtype=torch.float32, device=ys[0].device)
+        with torch.cuda.device(ys[0].device):
+            _lib.check(lib.sglb200_relu_concat(_lib.ptr_array([y.data_ptr() for y in ys]), len(ys), B, h, c_void_p(out.data_ptr()),
+                                               c_void_p(torch.cuda.current_stream().cuda_stream)), "relu_concat")
+        ctx.save_for_backward(*ys)
+        return out
+
+    @staticmethod
+    def backward(ctx, grad_out):
+        lib = _lib.load()
+        ys = ctx.saved_tensors
+        B, h = int(ys[0].shape[0]), int(ys[0].shape[1])
+        grad_out = grad_out.contiguous().float()
+        grads = [torch.empty_like(y) for y in ys]
+        with torch.cuda.device(ys[0].device):
+            _lib.check(lib.sglb200_relu_concat_backward(_lib.ptr_array([y.data_ptr() for y in ys]), len(ys), B, h,
+                                                        c_void_p(grad_out.data_ptr()), _lib.ptr_array([g.data_ptr() for g in grads]),
+                                                        c_void_p(torch.cuda.current_stream().cuda_stream)), "relu_concat_backward")
+        return tuple(grads)
+
+
 class IterateLearnableWeightedMessageOp(MessageOp):
     """Recursive gated combination (reference iterate_learnable_weighted_message_op.py:8-51)."""
 
@@ -146,8 +219,18 @@ class IterateLearnableWeightedMessageOp(MessageOp):
             raise ValueError("Invalid parameter numbers for the recursive iterate weighted aggregator!")
         self._learnable_weight = Linear(2 * args[0], 1)
 
+    fused = True   # CUDA batches go through the fused kernels (csrc/iterate.cu); False keeps the torch expression
+
     def _combine(self, feat_list):
         s, e = self._start, self._end
+        if s > 0 and e > s:
+            # the reference indexes the running weight matrix with ABSOLUTE hop numbers (:44-46: `for j in range(1, i + 1)`
+            # with i starting at `start`), so start > 0 reads column 1 of a one-column matrix: same failure here
+            raise IndexError("index 1 is out of bounds for dimension 1 with size 1")
+        sel = feat_list[s:e]
+        if self.fused and sel and all(f.is_cuda for f in sel) and 1 <= len(sel) <= 16 \
+                and len({tuple(f.shape) for f in sel}) == 1:
+            return _FusedIterate.apply(self._learnable_weight.weight, self._learnable_weight.bias, *sel)
         combined = feat_list[s]
         scores = None
         for i in range(s, e):
@@ -193,8 +276,12 @@ class ProjectedConcatMessageOp(MessageOp):
         self._learnable_weight = ModuleList(
             _Mlp(feat_dim, hidden_dim, num_layers, hidden_dim) for _ in range(end - start))
 
+    fused = True   # CUDA batches: ReLU + concat in one kernel (csrc/iterate.cu); the per-hop MLPs stay dense torch layers
+
     def _combine(self, feat_list):
         sel = feat_list[self._start:self._end]
+        if self.fused and sel and all(f.is_cuda for f in sel) and len(sel) <= 16:
+            return _FusedReluConcat.apply(*[mlp(f) for mlp, f in zip(self._learnable_weight, sel)])
         parts = [self._learnable_weight[0](sel[0])]
         parts += [F.relu(mlp(f)) for mlp, f in zip(list(self._learnable_weight)[1:], sel[1:])]
         return torch.hstack(parts)

@@ -159,6 +159,22 @@ class CsrOperator:
                                        _MODES[mode], int(accumulate), _stream_ptr()), "spmm")
         return out
 
+    def spmm_axpby(self, x: torch.Tensor, alpha: float, res: Optional[torch.Tensor] = None, clamp=None, mode="fast",
+                   out: Optional[torch.Tensor] = None):
+        """out = clamp(alpha * (A x) + res, *clamp) in one launch (label propagation layer, sglb200_spmm_axpby)."""
+        x = x.contiguous()
+        d = int(x.shape[1])
+        if out is None:
+            out = torch.empty((self.shape[0], d), dtype=torch.float32, device=x.device)
+        if res is not None:
+            res = res.contiguous()
+        lo, hi = (float(clamp[0]), float(clamp[1])) if clamp is not None else (0.0, 0.0)
+        with torch.cuda.device(self.device):
+            check(_lib.load().sglb200_spmm_axpby(self._h, c_void_p(x.data_ptr()), d, c_void_p(out.data_ptr()), d, d, _MODES[mode],
+                                                 float(alpha), None if res is None else c_void_p(res.data_ptr()), d,
+                                                 int(clamp is not None), lo, hi, _stream_ptr()), "spmm_axpby")
+        return out
+
     def chunks(self, n_chunks: int, mode="fast"):
         """(tile_bounds, row_bounds) of n_chunks consecutive tile ranges of the schedule (sglb200_graph_chunks)."""
         tb = (c_int64 * (n_chunks + 1))()

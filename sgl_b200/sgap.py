@@ -40,6 +40,10 @@ class BaseSGAPModel(nn.Module):
     # stay resident and are gathered per mini-batch on the device).  Set to False for the reference's exact data flow
     # (K+1 CPU tensors in _processed_feat_list).
     fused_preprocess = True
+    # combiners whose fused row flush needs a read-modify-write per row (running max / min, NAFS weights): measured slower
+    # than K plain hops + one streaming aggregation kernel (profiles/r02_fused_driver.txt), so preprocess takes that route
+    unfused_aggregates = ("max", "min", "osd")
+    fuse_when_slabs_exceed = 0.5   # fraction of the free HBM above which the K+1 hop slabs are not materialised
     feature_device = "cpu"   # where _processed_feature lives after a fused preprocess ("cpu" like the reference | "cuda")
 
     def preprocess(self, adj, feature):
@@ -53,6 +57,15 @@ class BaseSGAPModel(nn.Module):
         if self.fused_preprocess and not self._pre_msg_learnable and hasattr(self._pre_msg_op, "fused_spec") \
                 and hasattr(self._pre_graph_op, "propagate_aggregate_device") and feature.shape[1] <= 512:
             spec = self._pre_msg_op.fused_spec(self._prop_steps)
+            if spec is not None and spec.get("agg") not in ("last", "concat"):
+                # last / concat cost nothing extra (the hop kernel just stores elsewhere).  The running aggregates are
+                # measured slower than K plain hops + ONE streaming aggregation kernel (products-shape: 38.8 vs 33.9 ms for
+                # sum/mean/weighted, 60 vs 39 ms for the NAFS weights; profiles/r02_fused_driver.txt) but need no K+1 slabs:
+                # they are the route when the slabs would not fit comfortably in HBM
+                slabs = (self._prop_steps + 1) * feature.shape[0] * feature.shape[1] * 4
+                free, _ = torch.cuda.mem_get_info()
+                if slabs <= self.fuse_when_slabs_exceed * free or spec.get("agg") in self.unfused_aggregates:
+                    spec = None
         if spec is not None:
             # one pass per hop: normalisation, per-hop store (none needed) and the combiner run inside the hop kernel
             _, out = self._pre_graph_op.propagate_aggregate_device(adj, feature, spec)

@@ -22,8 +22,12 @@ from .graph_build import normalized_adjacency_device
 from .runtime import CsrOperator, aggregate, require_cuda
 
 
+def _default_clamp(x):
+    return x.clamp_(0., 1.)
+
+
 @torch.no_grad()
-def label_propagation(labels, adj, num_layers, alpha, post_process: Callable = lambda x: x.clamp_(0., 1.), mask=None,
+def label_propagation(labels, adj, num_layers, alpha, post_process: Callable = _default_clamp, mask=None,
                       mode: str = "fast"):
     """Same signature and semantics as the reference's label_propagation: `adj` is the already normalised scipy matrix
     (cast to float32 like sparse_mx_to_torch_sparse_tensor does), labels a long vector or a float matrix."""
@@ -41,9 +45,13 @@ def label_propagation(labels, adj, num_layers, alpha, post_process: Callable = l
     op = CsrOperator.from_scipy(adj.tocsr())
     try:
         res = (1 - alpha) * out
+        fused = post_process is _default_clamp and alpha != 0 and out.shape[1] <= 512
         for _ in range(num_layers):
-            out = alpha * op.spmm(out.contiguous(), mode=mode) + res
-            out = post_process(out)
+            if fused:   # scale, residual add and clamp inside the hop kernel's row flush: one launch per layer
+                out = op.spmm_axpby(out, alpha, res, clamp=(0.0, 1.0), mode=mode)
+            else:
+                out = alpha * op.spmm(out.contiguous(), mode=mode) + res
+                out = post_process(out)
     finally:
         op.close()
     return out.cpu() if on_cpu else out
@@ -92,3 +100,52 @@ def nafs_smoothed_features(adj, features, hops: int, r_list: Sequence[float] = (
     if method == "concat":
         return torch.cat(per_r, dim=1).cpu()
     return per_r[-1].cpu()
+
+
+@torch.no_grad()
+def nafs_smoothed_features_sweep(adj, features, max_hops: int, r_list: Sequence[float] = (0.5, 0.4, 0.3, 0.2, 0.1, 0.0),
+                                 method: str = "mean", mode: str = "fast"):
+    """[nafs_smoothed_features(adj, features, h, ...) for h in 1..max_hops] with every hop computed ONCE per r.
+    The reference's NAFS tasks call the feature construction from scratch for every hop count
+    (sgl/tasks/node_clustering.py:177-179, link_prediction.py:163-165): O(max_hops^2 * len(r_list)) hops.  The hop list of
+    h+1 is the hop list of h plus one more hop, so one propagation of max_hops hops per r serves the whole sweep; only the
+    over-smoothing-distance combination (a streaming kernel over h+1 slabs) is repeated per hop count."""
+    if method not in ("mean", "max", "concat", "simple"):
+        raise ValueError("method must be 'mean', 'max', 'concat' or 'simple'")
+    require_cuda()
+    dev = torch.device("cuda", torch.cuda.current_device())
+    x = torch.as_tensor(np.asarray(features) if not isinstance(features, torch.Tensor) else features,
+                        dtype=torch.float32).to(dev).contiguous()
+    coo = adj.tocoo()
+    parts = normalized_adjacency_device(torch.from_numpy(coo.row.astype(np.int64)).to(dev),
+                                        torch.from_numpy(coo.col.astype(np.int64)).to(dev), adj.shape[0],
+                                        torch.from_numpy(np.asarray(coo.data, dtype=np.float32)).to(dev), r=float(r_list[0]))
+    op = CsrOperator(parts["indptr"], parts["indices"], None, adj.shape)
+    deg = parts["deg"].cpu().numpy()
+    per_hop = [[] for _ in range(max_hops)]          # per_hop[h-1] = one tensor per r
+    try:
+        for r in (r_list[:1] if method == "simple" else r_list):
+            with np.errstate(divide="ignore", invalid="ignore"):
+                dl, dr = np.power(deg, r - 1), np.power(deg, -r)
+            dl[np.isinf(dl)] = 0.0
+            dr[np.isinf(dr)] = 0.0
+            op.normalize_values(parts["raw_w"], torch.from_numpy(dl).to(dev), torch.from_numpy(dr).to(dev))
+            hop_list = op.propagate(x, max_hops, mode=mode)
+            for h in range(1, max_hops + 1):
+                per_hop[h - 1].append(hop_list[h] if method == "simple" else aggregate(_lib.AGG_OSD, hop_list[:h + 1]))
+    finally:
+        op.close()
+    outs = []
+    for per_r in per_hop:
+        if method == "mean":
+            acc = per_r[0].clone()
+            for t in per_r[1:]:
+                acc = acc + t
+            outs.append((acc / len(per_r)).cpu())
+        elif method == "max":
+            outs.append(torch.stack(per_r, dim=0).max(0)[0].cpu())
+        elif method == "concat":
+            outs.append(torch.cat(per_r, dim=1).cpu())
+        else:
+            outs.append(per_r[-1].cpu())
+    return outs

@@ -197,6 +197,8 @@ def _feature_split_worker(rank, world, port, d, K, out_dir):
         hops = op.propagate(torch.from_numpy(x[:, cb[rank]:cb[rank + 1]].copy()), K)
         full = op.gather_columns(hops[-1], d)
         np.save(os.path.join(out_dir, f"fs_{rank}.npy"), full.numpy())
+        shard = op.rows_from_columns(hops[-1], d)          # the all-to-all form: this rank's rows, all columns
+        np.save(os.path.join(out_dir, f"fs_rows_{rank}.npy"), shard.numpy())
     finally:
         dist.destroy_process_group()
 
@@ -212,5 +214,7 @@ def test_feature_split_needs_no_exchange_and_matches(tmp_path, world, d):
     a = _graph(9)
     x = np.random.default_rng(10).standard_normal((a.shape[0], d)).astype(np.float32)
     ref = O.propagate(a, x, K, "fma")[-1]
+    rb = FeatureSplitOperator.row_bounds(a.shape[0], world)
     for r in range(world):
         assert np.array_equal(np.load(tmp_path / f"fs_{r}.npy"), ref)   # column blocks are independent: bit-exact
+        assert np.array_equal(np.load(tmp_path / f"fs_rows_{r}.npy"), ref[rb[r]:rb[r + 1]])

@@ -495,9 +495,10 @@ def test_sgap_models_preprocess_and_forward():
              (sgap.GBP(K, d, 4, 16, 2).cuda(),
               O.combine_weighted(ref, O.alpha_weights(K + 1, 0.85, 0, K + 1), 0, K + 1)),
              (sgap.SIGN(K, d, 4, 16, 2).cuda(), O.combine_concat(ref, 0, K + 1))]
-    for fused in (True, False):
+    for fused, threshold in ((True, 0.5), (True, 0.0), (False, 0.5)):   # 0.0: always take the memory-lean fused aggregates
         for model, want in cases:
             model.fused_preprocess = fused
+            model.fuse_when_slabs_exceed = threshold
             model._pre_graph_op.mode = "exact"
             model.preprocess(adj, x)
             feat = model._processed_feature
@@ -644,6 +645,16 @@ def test_label_propagation_and_nafs_features():
         want = O.nafs_smoothed_features(adj, x, 3, (0.5, 0.3, 0.0), method)
         assert got.shape == want.shape
         np.testing.assert_allclose(got, want, rtol=2e-5, atol=4e-6, err_msg=method)
+    # the hop sweep of the NAFS tasks: every hop computed once per r, equal to the per-hop-count calls
+    from sgl_b200.tricks import nafs_smoothed_features_sweep
+    sweep = nafs_smoothed_features_sweep(adj, x, 3, r_list=(0.5, 0.0), method="mean")
+    for h in (1, 2, 3):
+        single = nafs_smoothed_features(adj, x, hops=h, r_list=(0.5, 0.0), method="mean")
+        assert torch.equal(sweep[h - 1], single), h
+    # a user post_process keeps the unfused layer sequence; the default clamp takes the fused hop (same numbers)
+    plain = label_propagation(y, norm, num_layers=5, alpha=0.8, mask=mask, post_process=lambda t: t.clamp_(0., 1.))
+    want_lp = O.label_propagation(onehot, O.laplacian_adj(adj, 0.5), 5, 0.8, mask=mask.numpy())
+    np.testing.assert_allclose(plain.numpy(), want_lp, rtol=1e-5, atol=1e-6)
 
 
 # --------------------------------------------------------------------------------------------------------------
@@ -755,3 +766,98 @@ def test_message_ops_keep_the_autograd_graph():
     assert all(f.grad is not None for f in feats)
     with torch.no_grad():
         assert not SumMessageOp(0, 4).aggregate(feats).requires_grad
+
+
+# --------------------------------------------------------------------------------------------------------------
+# a12: IterateLearnableWeightedMessageOp / ProjectedConcatMessageOp fused kernels vs the reference's torch expressions
+# --------------------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("se", [(0, 5), (0, 3), (0, 1)])
+@pytest.mark.parametrize("d", [16, 100])
+def test_fused_iterate_learnable_forward_and_gradients(se, d):
+    """csrc/iterate.cu against the torch expression restating iterate_learnable_weighted_message_op.py:28-51 (itself pinned
+    to the reference's goldens on the CPU, tests/test_host_logic.py): outputs 1e-5, gradients 1e-4 (relative)."""
+    from sgl_b200.operators.message_op import IterateLearnableWeightedMessageOp
+    torch.manual_seed(3 + d)
+    B, n_all = 700, 5
+    s, e = se
+    op = IterateLearnableWeightedMessageOp(s, e, "recursive", d).cuda()
+    with torch.no_grad():
+        op._learnable_weight.weight.mul_(3.0)       # gates away from 0.5 so that the recursion matters
+    feats_a = [torch.randn(B, d, device="cuda", requires_grad=True) for _ in range(n_all)]
+    feats_b = [f.detach().clone().requires_grad_(True) for f in feats_a]
+    g = torch.randn(B, d, device="cuda")
+    op.fused = True
+    out_a = op.aggregate(feats_a)
+    (out_a * g).sum().backward()
+    gw_a, gb_a = op._learnable_weight.weight.grad.clone(), op._learnable_weight.bias.grad.clone()
+    op.zero_grad()
+    op.fused = False
+    out_b = op.aggregate(feats_b)
+    (out_b * g).sum().backward()
+    gw_b, gb_b = op._learnable_weight.weight.grad, op._learnable_weight.bias.grad
+
+    def close(x, y, tol):
+        scale = max(float(y.abs().max()), 1e-12)
+        assert float((x - y).abs().max()) <= tol * scale, (float((x - y).abs().max()), scale)
+
+    close(out_a, out_b, 1e-5)
+    for k in range(n_all):
+        if s <= k < e:
+            close(feats_a[k].grad, feats_b[k].grad, 1e-4)
+        else:
+            assert feats_a[k].grad is None and feats_b[k].grad is None
+    close(gw_a, gw_b, 1e-4)
+    close(gb_a, gb_b, 1e-4)
+    with pytest.raises(IndexError):      # start > 0 fails in the reference (absolute hop index into the weight matrix)
+        IterateLearnableWeightedMessageOp(1, 4, "recursive", d).cuda().aggregate(feats_a)
+
+
+def test_fused_projected_concat_matches_torch():
+    from sgl_b200.operators.message_op import ProjectedConcatMessageOp
+    torch.manual_seed(11)
+    B, d, h = 300, 24, 12
+    op = ProjectedConcatMessageOp(0, 4, d, h, 2).cuda().eval()    # eval: dropout off, both paths deterministic
+    feats_a = [torch.randn(B, d, device="cuda", requires_grad=True) for _ in range(4)]
+    feats_b = [f.detach().clone().requires_grad_(True) for f in feats_a]
+    g = torch.randn(B, 4 * h, device="cuda")
+    op.fused = True
+    out_a = op.aggregate(feats_a)
+    (out_a * g).sum().backward()
+    grads_a = [p.grad.clone() for p in op.parameters()]
+    op.zero_grad()
+    op.fused = False
+    out_b = op.aggregate(feats_b)
+    (out_b * g).sum().backward()
+    assert torch.equal(out_a, out_b)
+    for fa, fb in zip(feats_a, feats_b):
+        assert torch.allclose(fa.grad, fb.grad, rtol=1e-5, atol=1e-6)
+    for ga, pb in zip(grads_a, op.parameters()):
+        assert torch.allclose(ga, pb.grad, rtol=1e-5, atol=1e-6)
+
+
+def test_hop_cache_miss_compute_save_hit_on_gpu(tmp_path):
+    """f4: GraphOp.cache_dir on hardware -- a miss runs the K hops on the GPU and stores them, a hit returns the same bits
+    without touching the operator; a different graph op parameter misses again."""
+    rng = np.random.default_rng(61)
+    n, d, K = 800, 24, 3
+    adj = random_graph(rng, n, 6000)
+    x = rng.standard_normal((n, d)).astype(np.float32)
+    ref = O.propagate(O.laplacian_adj(adj, 0.5), x, K, "fma")
+    op = LaplacianGraphOp(K, r=0.5)
+    op.mode = "exact"
+    op.cache_dir = str(tmp_path)
+    first = op.propagate(adj, x)                      # miss -> GPU -> save
+    assert len(os.listdir(tmp_path)) == 1
+    for k in range(K + 1):
+        assert np.array_equal(first[k].numpy(), ref[k])
+    op2 = LaplacianGraphOp(K, r=0.5)
+    op2.mode = "exact"
+    op2.cache_dir = str(tmp_path)
+    second = op2.propagate(adj, x)                    # hit: no operator is built
+    assert op2._operator is None and op2._adj is not None
+    assert all(np.array_equal(a.numpy(), b.numpy()) for a, b in zip(first, second))
+    assert second[0].numpy().ctypes.data == x.ctypes.data     # element 0 still aliases the caller's array
+    op3 = LaplacianGraphOp(K, r=0.3)
+    op3.cache_dir = str(tmp_path)
+    op3.propagate(adj, x)
+    assert len(os.listdir(tmp_path)) == 2 and op3._operator is not None

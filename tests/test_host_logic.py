@@ -196,3 +196,28 @@ def test_hop_cache_round_trip_and_content_keys(tmp_path):
     HopCache(str(tmp_path)).save(HopCache.key(adj, x, "LaplacianGraphOp:" + op.mode, 3, r=0.5, alpha=None), hops)
     got = op.propagate(adj, x)
     assert all(torch.equal(a, b) for a, b in zip(got, hops)) and got[0].data_ptr() == torch.from_numpy(x).data_ptr()
+
+
+def test_custom_homo_layout_round_trip(tmp_path):
+    """sgl_b200.io writes the raw files the reference's Custom_Homo reads (custom_dataset.py:38-85) and reads them back
+    into the adjacency the hot path takes (duplicates summed like base_data.py:29-30)."""
+    import scipy.sparse as sp
+    from sgl_b200 import io
+    rng = np.random.default_rng(0)
+    n = 50
+    row, col = rng.integers(0, n, 300), rng.integers(0, n, 300)
+    w = np.ones(300, dtype=np.float32)
+    x = rng.standard_normal((n, 6)).astype(np.float32)
+    y = np.eye(4)[rng.integers(0, 4, n)]
+    d = io.write_custom_homo(str(tmp_path), "toy", (row, col, w), x, y, train_idx=np.arange(10), test_idx=np.arange(10, 20))
+    assert sorted(os.listdir(d)) == ["adj_matrix.npz", "indices.npz", "label.npy", "x.npy"]
+    f = np.load(os.path.join(d, "adj_matrix.npz"))
+    assert set(f.files) == {"row", "col", "data"}
+    got = io.read_custom_homo(str(tmp_path), "toy")
+    want = sp.csr_matrix((w, (row, col)), shape=(n, n))
+    want.sum_duplicates()
+    assert (got["adj"] != want).nnz == 0 and got["adj"].dtype == np.float32
+    assert np.array_equal(got["x"], x) and np.array_equal(got["y"], y.argmax(1))
+    assert np.array_equal(got["train_idx"], np.arange(10)) and got["val_idx"] is None
+    with pytest.raises(ValueError):
+        io.read_custom_homo(str(tmp_path), "missing", num_node=5)
