@@ -21,4 +21,4 @@ PY
 }
 run products_feature "$@"
 run products_row --partition row --transport nccl "$@"
-run rmat23_feature --workload rmat23 "$@"
+if [ "$N" -le 4 ]; then run rmat23_feature --workload rmat23 "$@"; fi

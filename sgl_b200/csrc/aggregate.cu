@@ -101,6 +101,99 @@ __device__ __forceinline__ float warp_sum(float v)
 
 // NAFS over-smoothing-distance weights (over_smooth_distance_op.py:11-33); feats[0] is the reference feature X.
 //   c_k = <x, y_k> / (|y_k| + 1e-10) / (|x| + 1e-10);  w = softmax_k(c);  out = sum_k w_k * y_k   (hop order)
+// One warp per node.  NV float4 slices per lane cover the row (d <= 128 NV); the hop rows are fetched FOUR AT A TIME
+// (4 NV independent 128-bit loads in flight per lane) and their dot products / norms are reduced together, so the
+// kernel streams instead of waiting out one load-reduce chain per hop; the second pass (weighted sum) re-reads rows that
+// are still in L1/L2.  Bytes: (K'+1) N d 4 from HBM.
+template <int NV>
+__global__ void __launch_bounds__(256) agg_osd_vec_kernel(const FeatPtrs f, int n_feats, int64_t n, int d, int64_t ld_in,
+                                                          float *__restrict__ out, int64_t ld_out)
+{
+    __shared__ float s_c[8][kMaxFeats];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int64_t row = (int64_t)blockIdx.x * 8 + warp;
+    if (row >= n) return;
+    bool act[NV];
+    float4 x[NV];
+    float nx = 0.0f;
+#pragma unroll
+    for (int v = 0; v < NV; ++v) {
+        const int c = (v * 32 + lane) * 4;
+        act[v] = c < d;
+        x[v] = act[v] ? __ldg(reinterpret_cast<const float4 *>(f.p[0] + row * ld_in + c)) : make_float4(0, 0, 0, 0);
+        nx = fmaf(x[v].x, x[v].x, fmaf(x[v].y, x[v].y, fmaf(x[v].z, x[v].z, fmaf(x[v].w, x[v].w, nx))));
+    }
+    nx = sqrtf(warp_sum(nx)) + 1e-10f;
+    float cmax = -INFINITY;
+    for (int k0 = 0; k0 < n_feats; k0 += 4) {
+        float4 y[4][NV];
+#pragma unroll
+        for (int q = 0; q < 4; ++q)
+#pragma unroll
+            for (int v = 0; v < NV; ++v)
+                y[q][v] = (k0 + q < n_feats && act[v])
+                              ? __ldcs(reinterpret_cast<const float4 *>(f.p[k0 + q] + row * ld_in + (v * 32 + lane) * 4))
+                              : make_float4(0, 0, 0, 0);
+        float dot[4], ny[4];
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+            dot[q] = 0.0f;
+            ny[q] = 0.0f;
+#pragma unroll
+            for (int v = 0; v < NV; ++v) {
+                dot[q] = fmaf(x[v].x, y[q][v].x, fmaf(x[v].y, y[q][v].y, fmaf(x[v].z, y[q][v].z, fmaf(x[v].w, y[q][v].w, dot[q]))));
+                ny[q] = fmaf(y[q][v].x, y[q][v].x, fmaf(y[q][v].y, y[q][v].y, fmaf(y[q][v].z, y[q][v].z, fmaf(y[q][v].w, y[q][v].w, ny[q]))));
+            }
+        }
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1)
+#pragma unroll
+            for (int q = 0; q < 4; ++q) {
+                dot[q] += __shfl_xor_sync(0xffffffffu, dot[q], o);
+                ny[q] += __shfl_xor_sync(0xffffffffu, ny[q], o);
+            }
+#pragma unroll
+        for (int q = 0; q < 4; ++q)
+            if (k0 + q < n_feats) {
+                const float ck = __fdiv_rn(__fdiv_rn(dot[q], sqrtf(ny[q]) + 1e-10f), nx);
+                if (lane == 0) s_c[warp][k0 + q] = ck;
+                cmax = fmaxf(cmax, ck);
+            }
+    }
+    __syncwarp();
+    float denom = 0.0f;
+    for (int k = 0; k < n_feats; ++k) denom += expf(s_c[warp][k] - cmax);
+    float4 acc[NV];
+#pragma unroll
+    for (int v = 0; v < NV; ++v) acc[v] = make_float4(0, 0, 0, 0);
+    for (int k0 = 0; k0 < n_feats; k0 += 4) {
+        float4 y[4][NV];
+#pragma unroll
+        for (int q = 0; q < 4; ++q)
+#pragma unroll
+            for (int v = 0; v < NV; ++v)
+                y[q][v] = (k0 + q < n_feats && act[v])
+                              ? __ldg(reinterpret_cast<const float4 *>(f.p[k0 + q] + row * ld_in + (v * 32 + lane) * 4))
+                              : make_float4(0, 0, 0, 0);
+#pragma unroll
+        for (int q = 0; q < 4; ++q)
+            if (k0 + q < n_feats) {
+                const float wk = __fdiv_rn(expf(s_c[warp][k0 + q] - cmax), denom);
+#pragma unroll
+                for (int v = 0; v < NV; ++v) {
+                    acc[v].x = __fadd_rn(acc[v].x, __fmul_rn(wk, y[q][v].x));
+                    acc[v].y = __fadd_rn(acc[v].y, __fmul_rn(wk, y[q][v].y));
+                    acc[v].z = __fadd_rn(acc[v].z, __fmul_rn(wk, y[q][v].z));
+                    acc[v].w = __fadd_rn(acc[v].w, __fmul_rn(wk, y[q][v].w));
+                }
+            }
+    }
+#pragma unroll
+    for (int v = 0; v < NV; ++v)
+        if (act[v]) *reinterpret_cast<float4 *>(out + row * ld_out + (v * 32 + lane) * 4) = acc[v];
+}
+
+// generic widths / alignments: scalar lanes
 __global__ void __launch_bounds__(256) agg_osd_kernel(const FeatPtrs f, int n_feats, int64_t n, int d, int64_t ld_in,
                                                       float *__restrict__ out, int64_t ld_out)
 {
@@ -210,7 +303,10 @@ int sglb200_aggregate(int op, const float *const *feats, int n_feats, int64_t n,
         else agg_concat_kernel<1><<<blocks, threads, 0, stream>>>(f, n_feats, n, d, ld_in, out, ld_out);
         break;
     case SGLB200_AGG_OSD:
-        agg_osd_kernel<<<(unsigned)((n + 7) / 8), 256, 0, stream>>>(f, n_feats, n, d, ld_in, out, ld_out);
+        if (vec4 && d <= 128) agg_osd_vec_kernel<1><<<(unsigned)((n + 7) / 8), 256, 0, stream>>>(f, n_feats, n, d, ld_in, out, ld_out);
+        else if (vec4 && d <= 256) agg_osd_vec_kernel<2><<<(unsigned)((n + 7) / 8), 256, 0, stream>>>(f, n_feats, n, d, ld_in, out, ld_out);
+        else if (vec4 && d <= 512) agg_osd_vec_kernel<4><<<(unsigned)((n + 7) / 8), 256, 0, stream>>>(f, n_feats, n, d, ld_in, out, ld_out);
+        else agg_osd_kernel<<<(unsigned)((n + 7) / 8), 256, 0, stream>>>(f, n_feats, n, d, ld_in, out, ld_out);
         break;
     }
 #undef AGG_LAUNCH

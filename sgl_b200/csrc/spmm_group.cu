@@ -18,9 +18,13 @@ namespace sglb200 {
 // FLAG: the column stream is the tagged one (bit 31 = last non-zero of its row; graphs without empty rows): a row ends
 // where the stream says so, which turns the group-divergent row flush (window refill + shuffles) into a few predicated
 // instructions -- with 8 groups per warp the divergent flush was 70 % of the instruction stream.
-template <int G, int U, bool ACCUM, bool EPI = false, bool FLAG = false, int MINB = 3>
+// COOP (with FLAG): the (col, val) stream of ALL groups of a warp is fetched by the whole warp -- one coalesced load per
+// group and batch (1-2 cache lines) instead of every group reading 16 bytes of its own stream per instruction (8 lines):
+// the L1 tag stage was the busiest unit of the narrow-row hop (61 %), and a quarter of its work was this stream.
+template <int G, int U, bool ACCUM, bool EPI = false, bool FLAG = false, int MINB = 3, bool COOP = false>
 __global__ void __launch_bounds__(kWarpsPerBlock * 32, MINB) spmm_group_kernel(const __grid_constant__ SpmmParams p, const int32_t *__restrict__ idx_tag)
 {
+    static_assert(!COOP || FLAG, "the cooperative fetch walks the flagged stream");
     static_assert(!(FLAG && ACCUM), "the flagged walk starts every chain from zero");
     static_assert(!(EPI && ACCUM), "the fused row flush starts every chain from zero");
     constexpr int NG = 32 / G;             // tiles per warp
@@ -31,18 +35,23 @@ __global__ void __launch_bounds__(kWarpsPerBlock * 32, MINB) spmm_group_kernel(c
     static_assert(G == 4 || G == 8 || G == 16, "group width");
     static_assert(BATCH % U == 0, "U must divide the batch");
     __shared__ int2 s_pairs[kWarpsPerBlock][NG][PSTRIDE];
+    __shared__ int64_t s_j0[COOP ? kWarpsPerBlock : 1][NG];
+    __shared__ int s_nnz[COOP ? kWarpsPerBlock : 1][NG];
     const int lane = threadIdx.x & 31;
     const int gl = lane & (G - 1);   // lane inside the group
     const int gid = lane / G;        // group inside the warp
     const unsigned gmask = (G == 32 ? 0xffffffffu : ((1u << G) - 1u)) << (gid * G);
-    const int64_t t = p.tile_begin + ((int64_t)blockIdx.x * kWarpsPerBlock + (threadIdx.x >> 5)) * NG + gid;
-    if (t >= p.n_tiles) return;      // whole groups leave; nothing below synchronises beyond the group
+    const int64_t t_raw = p.tile_begin + ((int64_t)blockIdx.x * kWarpsPerBlock + (threadIdx.x >> 5)) * NG + gid;
+    if (!COOP && t_raw >= p.n_tiles) return;   // whole groups leave; nothing below synchronises beyond the group
+    // cooperative fetch: groups past the last tile stay (they help loading) and walk an empty tile
+    const bool live = t_raw < p.n_tiles;
+    const int64_t t = live ? t_raw : p.n_tiles - 1;
     int2 *pairs = &s_pairs[threadIdx.x >> 5][gid][0];
 
-    int row = p.tile_row[t];
-    const int row_end = p.tile_row[t + 1];
+    int row = live ? p.tile_row[t] : 0;
+    const int row_end = live ? p.tile_row[t + 1] : 0;
     const int64_t j0 = p.tile_nnz[t];
-    const int n_nnz = (int)(p.tile_nnz[t + 1] - j0);
+    const int n_nnz = live ? (int)(p.tile_nnz[t + 1] - j0) : 0;
     const int n_rows = (int)p.n_rows;
 
     const int cofs = gl * 4;
@@ -57,11 +66,11 @@ __global__ void __launch_bounds__(kWarpsPerBlock * 32, MINB) spmm_group_kernel(c
     const int cofss[1] = {cofs};
     bool red_skip_first = false;   // lean flush + running aggregate: see spmm_flat_kernel
     if constexpr (!EPI) {
-        if (p.red_agg && p.fold) red_skip_first = p.head_run[t] >= 0;
+        if (p.red_agg && p.fold && live) red_skip_first = p.head_run[t] >= 0;
     }
     int cont_slot = -1;   // fused row flush: see spmm_flat_kernel
     if constexpr (EPI) {
-        if (p.fold) {
+        if (p.fold && live) {
             const int hr = p.head_run[t];
             if (hr >= 0) cont_slot = (int)(p.run_base[hr] + p.run_len[hr]);
         }
@@ -138,28 +147,81 @@ __global__ void __launch_bounds__(kWarpsPerBlock * 32, MINB) spmm_group_kernel(c
     // elements per instruction), one batch ahead of their publication
     int32_t col_next[R];
     float val_next[R];
-    auto fetch_batch = [&](int b) {
+    // cooperative form: slot q of this lane belongs to group q; BATCH == 16: lanes 0-15 hold columns, 16-31 values;
+    // BATCH == 32: every lane holds one column (coop_c) and one value (coop_v) per group
+    constexpr int CW = COOP ? NG : 1;
+    int32_t coop_c[CW];
+    int32_t coop_v[(COOP && BATCH == 32) ? NG : 1];
+    int n_groups = (n_nnz + U - 1) / U;
+    if constexpr (COOP) {
+        if (gl == 0) {
+            s_j0[threadIdx.x >> 5][gid] = j0;
+            s_nnz[threadIdx.x >> 5][gid] = n_nnz;
+        }
+        // warp-uniform trip count: every lane takes part in every batch's fetch
 #pragma unroll
-        for (int i = 0; i < R; ++i) {
-            const int nb = b * BATCH + i * G + gl;
-            col_next[i] = 0;
-            val_next[i] = 0.0f;
-            if (nb < n_nnz) {
-                col_next[i] = __ldg(cols + nb);
-                val_next[i] = p.vals ? __ldg(vals + nb) : 1.0f;
+        for (int o = 16; o > 0; o >>= 1) n_groups = max(n_groups, __shfl_xor_sync(kFull, n_groups, o));
+        __syncwarp();
+    }
+    auto fetch_batch = [&](int b) {
+        if constexpr (COOP) {
+            const int e = lane & (BATCH - 1);
+            const int idx = b * BATCH + e;
+#pragma unroll
+            for (int q = 0; q < NG; ++q) {
+                const int64_t base = s_j0[threadIdx.x >> 5][q];
+                const bool ok = idx < s_nnz[threadIdx.x >> 5][q];
+                if constexpr (BATCH == 16) {
+                    int32_t v = 0;
+                    if (ok) {
+                        if (lane < 16) v = __ldg(idx_tag + base + idx);
+                        else v = p.vals ? __float_as_int(__ldg(p.vals + base + idx)) : __float_as_int(1.0f);
+                    }
+                    coop_c[q] = v;
+                } else {
+                    coop_c[q] = ok ? __ldg(idx_tag + base + idx) : 0;
+                    coop_v[q] = ok ? (p.vals ? __float_as_int(__ldg(p.vals + base + idx)) : __float_as_int(1.0f)) : 0;
+                }
+            }
+        } else {
+#pragma unroll
+            for (int i = 0; i < R; ++i) {
+                const int nb = b * BATCH + i * G + gl;
+                col_next[i] = 0;
+                val_next[i] = 0.0f;
+                if (nb < n_nnz) {
+                    col_next[i] = __ldg(cols + nb);
+                    val_next[i] = p.vals ? __ldg(vals + nb) : 1.0f;
+                }
             }
         }
     };
     fetch_batch(0);
     auto publish_batch = [&](int b) {
-        __syncwarp(gmask);  // the group is done with the batch that used this buffer two batches ago
+        if constexpr (COOP) {
+            __syncwarp();   // every group is done with the batch that used this buffer two batches ago
+            const int e = lane & (BATCH - 1);
 #pragma unroll
-        for (int i = 0; i < R; ++i) pairs[(b & 1) * BATCH + i * G + gl] = make_int2(col_next[i], __float_as_int(val_next[i]));
-        __syncwarp(gmask);
-        fetch_batch(b + 1);
+            for (int q = 0; q < NG; ++q) {
+                int32_t *dst = reinterpret_cast<int32_t *>(&s_pairs[threadIdx.x >> 5][q][(b & 1) * BATCH + e]);
+                if constexpr (BATCH == 16) {
+                    dst[lane >> 4] = coop_c[q];          // .x for the column lanes, .y for the value lanes
+                } else {
+                    dst[0] = coop_c[q];
+                    dst[1] = coop_v[q];
+                }
+            }
+            __syncwarp();
+            fetch_batch(b + 1);
+        } else {
+            __syncwarp(gmask);  // the group is done with the batch that used this buffer two batches ago
+#pragma unroll
+            for (int i = 0; i < R; ++i) pairs[(b & 1) * BATCH + i * G + gl] = make_int2(col_next[i], __float_as_int(val_next[i]));
+            __syncwarp(gmask);
+            fetch_batch(b + 1);
+        }
     };
 
-    const int n_groups = (n_nnz + U - 1) / U;
 #pragma unroll 1
     for (int g = 0; g < n_groups; ++g) {
         const int pos = g * U;
@@ -192,6 +254,7 @@ __global__ void __launch_bounds__(kWarpsPerBlock * 32, MINB) spmm_group_kernel(c
         }
     }
     while (row < row_end) flush_row();
+    if (COOP && !live) return;
     const int32_t slot = p.carry_slot[t];
     if (slot >= 0 && act) {
         char *wrow = reinterpret_cast<char *>(p.carry_ws + (int64_t)slot * p.ws_ld);
@@ -260,8 +323,11 @@ static cudaError_t launch_group(const SpmmParams &p, bool accum, const int32_t *
     constexpr int NG = 32 / G;
     const int64_t tiles = p.n_tiles - p.tile_begin;
     const unsigned blocks = (unsigned)((tiles + (int64_t)kWarpsPerBlock * NG - 1) / ((int64_t)kWarpsPerBlock * NG));
+    static const char *coop_env = getenv("SGLB200_GROUP_COOP");
+    const bool coop = coop_env && atoi(coop_env) == 1;   // measured and rejected as default: d=16 1139 vs 1044 us (products), 799 vs 728 (rmat22)
     if (accum) spmm_group_kernel<G, U, true><<<blocks, kWarpsPerBlock * 32, 0, stream>>>(p, nullptr);
     else if (p.epi.active && idx_tag) spmm_group_kernel<G, U, false, true, true><<<blocks, kWarpsPerBlock * 32, 0, stream>>>(p, idx_tag);
+    else if (idx_tag && U == 8 && coop) spmm_group_kernel<G, U, false, false, true, 3, true><<<blocks, kWarpsPerBlock * 32, 0, stream>>>(p, idx_tag);
     else if (p.epi.active) spmm_group_kernel<G, U, false, true><<<blocks, kWarpsPerBlock * 32, 0, stream>>>(p, nullptr);
     else if (idx_tag && U == 4) spmm_group_kernel<G, U, false, false, true, 4><<<blocks, kWarpsPerBlock * 32, 0, stream>>>(p, idx_tag);
     else if (idx_tag) spmm_group_kernel<G, U, false, false, true><<<blocks, kWarpsPerBlock * 32, 0, stream>>>(p, idx_tag);
