@@ -221,7 +221,9 @@ SGLB200_API int sglb200_peer_status(void);
 
 /* ---- legacy ABI: drop-in for the reference's two shared objects ----------------------------------------------
  * Same symbols, same signatures, host pointers, `answer` is accumulated into (matmul.c:36-37).  Internally:
- * upload -> EXACT-mode kernel -> download.  int32 offsets as in the reference, but N*d may exceed 2^31. */
+ * upload -> EXACT-mode kernel -> download.  int32 offsets as in the reference, but N*d may exceed 2^31.
+ * The void symbol has no error channel: on failure it prints to stderr, keeps the text in sglb200_last_error() and fills
+ * `answer` with NaN (SGLB200_LEGACY_ABORT=1: abort() instead); it never returns a silently wrong buffer. */
 SGLB200_API void FloatCSRMulDenseOMP(float answer[], float data[], int indices[], int indptr[], float mat[], int mat_row,
                          int mat_col);
 SGLB200_API int FloatCSRMulDense(float answer[], int data_nnz, float data[], int indices[], int indptr[], float mat[],

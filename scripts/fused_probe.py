@@ -28,14 +28,14 @@ def plain():
     for k in range(1, K + 1):
         op.spmm(hops[k - 1], out=hops[k])
 print(f"{name}: plain K hops                          {t(plain):8.2f} ms")
-for label, kw in [("fused norm, keep all, no agg", dict(keep="all")),
-                  ("fused norm, keep none, no agg", dict(keep="none")),
+for label, kw in [("fused norm, keep all, no agg", dict(keep="all", fuse_norm=True)),
+                  ("fused norm, keep none, no agg", dict(keep="none", fuse_norm=True)),
                   ("vals stream, keep all, no agg", dict(keep="all", fuse_norm=False)),
                   ("vals stream, keep none, agg mean", dict(keep="none", agg="mean", fuse_norm=False)),
-                  ("fused norm, keep none, agg mean", dict(keep="none", agg="mean")),
-                  ("fused norm, keep none, agg last", dict(keep="none", agg="last")),
-                  ("fused norm, keep none, agg osd", dict(keep="none", agg="osd")),
-                  ("fused norm, keep none, agg concat", dict(keep="none", agg="concat"))]:
+                  ("fused norm, keep none, agg mean", dict(keep="none", agg="mean", fuse_norm=True)),
+                  ("fused norm, keep none, agg last", dict(keep="none", agg="last", fuse_norm=True)),
+                  ("fused norm, keep none, agg osd", dict(keep="none", agg="osd", fuse_norm=True)),
+                  ("fused norm, keep none, agg concat", dict(keep="none", agg="concat", fuse_norm=True))]:
     print(f"{name}: {label:38s} {t(lambda: op.propagate_fused(x, K, **kw)):8.2f} ms")
 from sgl_b200.runtime import aggregate
 from sgl_b200 import _lib

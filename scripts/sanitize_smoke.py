@@ -54,7 +54,8 @@ for kind, args in (("gate", (16,)), ("ori_ref", (16,)), ("jk", (3, 16))):
 from sgl_b200.graph_build import operator_from_scipy_device  # noqa: E402
 from sgl_b200.operators.message_op import IterateLearnableWeightedMessageOp  # noqa: E402
 opd = operator_from_scipy_device(adj, r=0.5, alpha=0.15, tile_items=32, split_threshold=8)   # fused normalisation + PPR
-opd.propagate_fused(torch.randn(n, 100, device="cuda"), 3, mode="fast", keep="all", agg="mean")
+opd.propagate_fused(torch.randn(n, 100, device="cuda"), 3, mode="fast", keep="all", agg="mean", fuse_norm=True)
+opd.propagate_fused(torch.randn(n, 100, device="cuda"), 3, mode="fast", keep="none", agg="mean")
 opd.close()
 it = IterateLearnableWeightedMessageOp(0, 4, "recursive", 16).cuda()
 it.aggregate(feats).sum().backward()

@@ -97,7 +97,7 @@ constexpr int64_t kStreamPad = 128;  // zeroed elements behind indices / values:
 int build_stream_tags(sglb200_graph *g, cudaStream_t stream);
 int build_schedule(sglb200_graph *g, Schedule *s, int64_t split_threshold, cudaStream_t stream);
 void free_schedule(Schedule *s);
-int ensure_carry_ws(sglb200_graph *g, size_t floats);
+int ensure_carry_ws(sglb200_graph *g, size_t floats, cudaStream_t stream);
 struct Epilogue;
 // one hop with every option of the fused driver: epi (NULL = plain store), raw_weights != 0 streams the raw weights
 // (or nothing when they are all 1) instead of the normalised values

@@ -218,18 +218,18 @@ int build_schedule(sglb200_graph *g, Schedule *s, int64_t split_threshold, cudaS
     return SGLB200_OK;
 }
 
-int ensure_carry_ws(sglb200_graph *g, size_t floats)
+int ensure_carry_ws(sglb200_graph *g, size_t floats, cudaStream_t stream)
 {
     if (floats <= g->carry_ws_floats) return SGLB200_OK;
     if (g->carry_ws) {
-        // earlier launches on other streams may still use the old buffer
-        SGL_CUDA_CHECK(cudaDeviceSynchronize());
-        cudaFree(g->carry_ws);
+        // stream-ordered: hops already enqueued on this stream keep the old buffer until they are done (hops of one handle
+        // are serialised on one stream, spmm_launch_ex); no device-wide synchronisation in the middle of a run
+        SGL_CUDA_CHECK(cudaFreeAsync(g->carry_ws, stream));
         g->bytes_resident -= g->carry_ws_floats * sizeof(float);
         g->carry_ws = nullptr;
         g->carry_ws_floats = 0;
     }
-    SGL_CUDA_CHECK(cudaMalloc(&g->carry_ws, floats * sizeof(float)));
+    SGL_CUDA_CHECK(cudaMallocAsync(&g->carry_ws, floats * sizeof(float), stream));
     g->carry_ws_floats = floats;
     g->bytes_resident += floats * sizeof(float);
     return SGLB200_OK;

@@ -57,9 +57,17 @@ void FloatCSRMulDenseOMP(float answer[], float data[], int indices[], int indptr
 {
     const int st = sglb200::legacy_hop(answer, data, indices, indptr, mat, mat_row, mat_col, 1);
     if (st != SGLB200_OK) {
-        // the reference signature has no error channel: fail loudly instead of returning a silently wrong buffer
+        // the reference signature has no error channel.  Never return a silently wrong buffer: the message goes to stderr
+        // and stays readable through sglb200_last_error(), and `answer` is filled with NaN so that every consumer sees the
+        // failure; SGLB200_LEGACY_ABORT=1 restores the hard stop (abort()) for batch jobs that prefer to die at the hop.
         fprintf(stderr, "libsglb200: FloatCSRMulDenseOMP failed (status %d): %s\n", st, sglb200_last_error());
-        abort();
+        const char *hard = getenv("SGLB200_LEGACY_ABORT");
+        if (hard && hard[0] == '1') abort();
+        if (answer && mat_row > 0 && mat_col > 0) {
+            const size_t count = (size_t)mat_row * (size_t)mat_col;
+            const float nan_value = __builtin_nanf("");
+            for (size_t i = 0; i < count; ++i) answer[i] = nan_value;
+        }
     }
 }
 

@@ -86,17 +86,17 @@ __global__ void __launch_bounds__(256) agg_init_kernel(const float *__restrict__
     }
 }
 
-static int ensure_ping(sglb200_graph *g, size_t floats, int need_aux)
+static int ensure_ping(sglb200_graph *g, size_t floats, int need_aux, cudaStream_t stream)
 {
     if (floats > g->ping_floats) {
-        SGL_CUDA_CHECK(cudaDeviceSynchronize());
+        // stream-ordered growth: earlier passes enqueued on this stream finish with the old slabs first
         for (int k = 0; k < 2; ++k) {
-            cudaFree(g->ping[k]);
+            if (g->ping[k]) SGL_CUDA_CHECK(cudaFreeAsync(g->ping[k], stream));
             g->ping[k] = nullptr;
         }
         g->bytes_resident -= 2 * g->ping_floats * sizeof(float);
         g->ping_floats = 0;
-        for (int k = 0; k < 2; ++k) SGL_CUDA_CHECK(cudaMalloc(&g->ping[k], floats * sizeof(float)));
+        for (int k = 0; k < 2; ++k) SGL_CUDA_CHECK(cudaMallocAsync(&g->ping[k], floats * sizeof(float), stream));
         g->ping_floats = floats;
         g->bytes_resident += 2 * floats * sizeof(float);
     }
@@ -181,7 +181,7 @@ int sglb200_propagate_fused(sglb200_graph_t g, const float *X, int64_t ldx, floa
     for (int k = 1; k <= K; ++k)
         if (!kept(k)) need_ping = true;
     {
-        const int st = ensure_ping(g, need_ping ? (size_t)n * (size_t)d : 0, agg_op == SGLB200_AGG_OSD);
+        const int st = ensure_ping(g, need_ping ? (size_t)n * (size_t)d : 0, agg_op == SGLB200_AGG_OSD, stream);
         if (st != SGLB200_OK) return st;
     }
     int epi_op = EPI_AGG_NONE;

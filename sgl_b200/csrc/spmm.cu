@@ -31,7 +31,8 @@ namespace sglb200 {
 
 // FLAG: the column stream is the tagged one (idx_tag: bit 31 = last non-zero of its row; graphs without empty rows), so a
 // row ends where the stream says so: no row-pointer window, no countdown -- fewer live registers, more resident warps.
-template <int VEC, int VPL, int U, bool ACCUM, int MINB, int PIPE, bool HINT = false, bool EPI = false, bool FLAG = false>
+template <int VEC, int VPL, int U, bool ACCUM, int MINB, int PIPE, bool HINT = false, bool EPI = false, bool FLAG = false,
+          bool RED = false>
 __global__ void __launch_bounds__(kWarpsPerBlock * 32, MINB) spmm_flat_kernel(const __grid_constant__ SpmmParams p, const int32_t *__restrict__ idx_tag)
 {
     static_assert(!(FLAG && ACCUM), "the flagged walk starts every chain from zero");
@@ -73,8 +74,8 @@ __global__ void __launch_bounds__(kWarpsPerBlock * 32, MINB) spmm_flat_kernel(co
     // lean flush with a running aggregate: the first flushed row of a tile that FINISHES a cut row is only a piece of that
     // row -- the aggregate gets the folded row from whoever completes the fold, not this piece
     bool red_skip_first = false;
-    if constexpr (!EPI) {
-        if (p.red_agg && p.fold) red_skip_first = p.head_run[t] >= 0;
+    if constexpr (RED) {
+        if (p.fold) red_skip_first = p.head_run[t] >= 0;
     }
     // fused row flush: a tile whose first row continues a cut row parks that piece in the workspace (slot after the
     // row's carriers) instead of flushing it; the tile that completes the row's arrivals performs the one real flush
@@ -147,9 +148,11 @@ __global__ void __launch_bounds__(kWarpsPerBlock * 32, MINB) spmm_flat_kernel(co
                 if (act[v]) {
                     if (p.stream_y) acc[v].store_streaming(ybase[v] + (uint64_t)(uint32_t)row * ldy_bytes);
                     else acc[v].store(ybase[v] + (uint64_t)(uint32_t)row * ldy_bytes);
-                    if (p.red_agg && !red_skip_first) red_row_slice<VEC>(p, (uint32_t)row, cofs_v[v], acc[v]);
+                    if constexpr (RED) {
+                        if (!red_skip_first) red_row_slice<VEC>(p, (uint32_t)row, cofs_v[v], acc[v]);
+                    }
                 }
-            red_skip_first = false;
+            if constexpr (RED) red_skip_first = false;
         }
         ++row;
         if constexpr (!FLAG) {
@@ -316,19 +319,22 @@ __global__ void __launch_bounds__(kWarpsPerBlock * 32, MINB) spmm_flat_kernel(co
                 const size_t ws_ld_bytes = (size_t)p.ws_ld * sizeof(float);
                 const uint32_t out_row = (uint32_t)p.run_row[run];
                 if constexpr (EPI) {
-                    // c0 + c1 + ... + finisher piece (slot n_carriers), then the one real flush of the row
+                    // finisher piece (slot n_carriers) + (c0 + c1 + ...): the SAME order as the plain kernel's fold, so a hop gives
+                    // the same bits whichever flush it went through; then the one real flush of the row
                     Slice<VEC> sum[VPL];
 #pragma unroll
                     for (int v = 0; v < VPL; ++v) {
                         sum[v].zero();
                         if (!act[v]) continue;
                         const size_t cb = (size_t)cofs_v[v] * sizeof(float);
-                        Slice<VEC> part;
-                        sum[v].load_l2(ws0 + cb);
-                        for (int u = 1; u <= n_carriers; ++u) {
+                        Slice<VEC> part, carried;
+                        carried.load_l2(ws0 + cb);
+                        for (int u = 1; u < n_carriers; ++u) {
                             part.load_l2(ws0 + (size_t)u * ws_ld_bytes + cb);
-                            sum[v].add(part);
+                            carried.add(part);
                         }
+                        sum[v].load_l2(ws0 + (size_t)n_carriers * ws_ld_bytes + cb);
+                        sum[v].add(carried);
                     }
                     RowPrefetch<VEC, VPL> pf2;
                     prefetch_row<VEC, VPL>(p, out_row, act, cofs_v, pf2);
@@ -351,7 +357,7 @@ __global__ void __launch_bounds__(kWarpsPerBlock * 32, MINB) spmm_flat_kernel(co
                         part.load_l2(yp);          // the finishing tile's partial
                         part.add(sum);             // Y = finisher + (c0 + c1 + ...): the order of the separate fold kernel
                         part.store(yp);
-                        if (p.red_agg) red_row_slice<VEC>(p, out_row, cofs_v[v], part);
+                        if constexpr (RED) red_row_slice<VEC>(p, out_row, cofs_v[v], part);
                     }
                 }
                 if (lane == 0) p.run_count[run] = 0u;  // ready for the next hop
@@ -624,6 +630,10 @@ static cudaError_t launch_flat(const SpmmParams &p, bool accum, dim3 grid, cudaS
         else spmm_flat_kernel<VEC, VPL, U, false, (MINB > 3 ? 3 : MINB), 1, false, true><<<grid, kWarpsPerBlock * 32, 0, stream>>>(p, nullptr);
         return cudaGetLastError();
     }
+    if (!accum && p.red_agg) {   // lean flush + running aggregate (L2 reductions)
+        spmm_flat_kernel<VEC, VPL, U, false, (MINB > 3 ? 3 : MINB), 1, false, false, false, true><<<grid, kWarpsPerBlock * 32, 0, stream>>>(p, nullptr);
+        return cudaGetLastError();
+    }
     if (!accum && tags && p.hub_cols == 0) {
         static int minb4 = env_int("SGLB200_FLAG_MINB4", 0);
         if (VEC == 4 && VPL == 1 && minb4) spmm_flat_kernel<VEC, VPL, U, false, (VEC == 4 && VPL == 1 ? 4 : MINB), 1, false, false, true><<<grid, kWarpsPerBlock * 32, 0, stream>>>(p, tags);
@@ -777,7 +787,7 @@ int spmm_launch_ex(sglb200_graph *g, const float *X, int64_t ldx, float *Y, int6
     }
     const int64_t ws_ld = (d + 3) & ~3;
     if (s->n_slots > 0) {
-        const int st = ensure_carry_ws(g, (size_t)s->n_slots * (size_t)ws_ld);
+        const int st = ensure_carry_ws(g, (size_t)s->n_slots * (size_t)ws_ld, stream);
         if (st != SGLB200_OK) return st;
     }
     SpmmParams p = {};
@@ -964,7 +974,7 @@ int spmm_launch_ex(sglb200_graph *g, const float *X, int64_t ldx, float *Y, int6
 static int ensure_stage(sglb200_graph *g, size_t floats)
 {
     if (floats <= g->stage_floats) return SGLB200_OK;
-    SGL_CUDA_CHECK(cudaDeviceSynchronize());
+    // propagate_host is synchronous (it returns after both of its streams are idle): nothing of this handle is in flight
     for (int k = 0; k < 3; ++k) {
         cudaFree(g->stage[k]);
         g->stage[k] = nullptr;

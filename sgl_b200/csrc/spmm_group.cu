@@ -283,12 +283,15 @@ __global__ void __launch_bounds__(kWarpsPerBlock * 32, MINB) spmm_group_kernel(c
                     const size_t cb = (size_t)cofs * sizeof(float);
                     Slice<4> sums[1], part;
                     sums[0].zero();
-                    if (act) {
-                        sums[0].load_l2(ws0 + cb);
-                        for (int u = 1; u <= n_carriers; ++u) {
+                    if (act) {   // finisher piece + (c0 + c1 + ...): the plain fold's order
+                        Slice<4> carried;
+                        carried.load_l2(ws0 + cb);
+                        for (int u = 1; u < n_carriers; ++u) {
                             part.load_l2(ws0 + (size_t)u * ws_ld_bytes + cb);
-                            sums[0].add(part);
+                            carried.add(part);
                         }
+                        sums[0].load_l2(ws0 + (size_t)n_carriers * ws_ld_bytes + cb);
+                        sums[0].add(carried);
                     }
                     RowPrefetch<4, 1> pf2;
                     prefetch_row<4, 1>(p, (uint32_t)p.run_row[run], acts, cofss, pf2);

@@ -253,12 +253,15 @@ __global__ void __launch_bounds__(kWarpsPerBlock * 32) spmm_tma_kernel(const __g
                     Slice<4> sum[1], part;
                     sum[0].zero();
                     if constexpr (EPI) {
-                        if (act1[0]) {
-                            sum[0].load_l2(ws0);
-                            for (int u = 1; u <= n_carriers; ++u) {
+                        if (act1[0]) {   // finisher piece + (c0 + c1 + ...): the plain fold's order
+                            Slice<4> carried;
+                            carried.load_l2(ws0);
+                            for (int u = 1; u < n_carriers; ++u) {
                                 part.load_l2(ws0 + (size_t)u * ws_ld_bytes);
-                                sum[0].add(part);
+                                carried.add(part);
                             }
+                            sum[0].load_l2(ws0 + (size_t)n_carriers * ws_ld_bytes);
+                            sum[0].add(carried);
                         }
                         RowPrefetch<4, 1> pf2;
                         prefetch_row<4, 1>(p, out_row, act1, cofs1, pf2);

@@ -219,13 +219,15 @@ class CsrOperator:
 
     # ---- K hops + degree normalisation + cross-hop aggregation in one pass per hop -----------------------------
     def propagate_fused(self, x: torch.Tensor, prop_steps: int, mode="fast", keep="none", agg: Optional[str] = None,
-                        start: int = 0, end: Optional[int] = None, weights=None, fuse_norm: bool = True):
+                        start: int = 0, end: Optional[int] = None, weights=None, fuse_norm: bool = False):
         """K hops through sglb200_propagate_fused.  keep: "none" | "last" | "all" -- which hops are stored;
         agg: None | "sum" | "mean" | "max" | "min" | "weighted" | "concat" | "osd" | "last" over hops [start, end)
         (reference message_op/*.py; weights: one float per hop 0..K for "weighted").  Returns (hops, out): hops is a list
         of K+1 entries (None where a hop was not stored; entry 0 is x), out the aggregate or None.
-        With fuse_norm and FAST mode on an operator built by sgl_b200.graph_build the normalised values are never read:
-        the kernel streams the raw weights and applies deg^(r-1) / deg^(-r) in the row flush."""
+        With fuse_norm=True and FAST mode on an operator built by sgl_b200.graph_build the normalised values are never
+        read: the kernel streams the raw weights and applies deg^(r-1) / deg^(-r) in the row flush.  Off by default: it
+        saves the value array (4 bytes per edge of HBM) but measures 35 % slower per hop than the exact-values stream on
+        products-shape (profiles/r02_fused_driver.txt)."""
         if self.shape[0] != self.shape[1]:
             raise ValueError("propagate needs a square operator")
         if not (isinstance(x, torch.Tensor) and x.is_cuda and x.dtype == torch.float32 and x.dim() == 2):

@@ -737,19 +737,32 @@ def test_fused_normalisation_fast_mode(kind, r, alpha, weighted, d):
     op = operator_from_scipy_device(adj, r=r, alpha=alpha, tile_items=64, split_threshold=24)
     assert op.info()["carry_runs"] > 0
     xd = torch.from_numpy(x).cuda()
-    hops, out = op.propagate_fused(xd, K, mode="fast", keep="all", agg="mean")
-    hops2, out2 = op.propagate_fused(xd, K, mode="fast", keep="all", agg="mean")
+    hops, out = op.propagate_fused(xd, K, mode="fast", keep="all", agg="mean", fuse_norm=True)
+    hops2, out2 = op.propagate_fused(xd, K, mode="fast", keep="all", agg="mean", fuse_norm=True)
     for k in range(1, K + 1):
         assert_close_1e5(hops[k].cpu().numpy(), ref[k])
         assert torch.equal(hops[k], hops2[k])
     assert_close_1e5(out.cpu().numpy(), O.combine_mean(ref, 0, K + 1))
     assert torch.equal(out, out2)
     # without keeping the hops (internal ping-pong slabs only) the aggregate is the same bits
-    _, out3 = op.propagate_fused(xd, K, mode="fast", keep="none", agg="mean")
+    _, out3 = op.propagate_fused(xd, K, mode="fast", keep="none", agg="mean", fuse_norm=True)
     assert torch.equal(out, out3)
     # fuse_norm=False streams the materialised float32 values: same tolerance, and EXACT stays bit-exact
     hops4, _ = op.propagate_fused(xd, K, mode="fast", keep="all", fuse_norm=False)
     assert_close_1e5(hops4[K].cpu().numpy(), ref[K])
+    # running mean on the LEAN flush (L2 reductions) with cut rows: the folded row, not its pieces, reaches the aggregate --
+    # bit-equal to the left-to-right mean of the very hops this mode produces
+    _, out4 = op.propagate_fused(xd, K, mode="fast", keep="none", agg="mean", fuse_norm=False)
+    want4 = hops4[0].clone() + 0.0
+    for k in range(1, K + 1):
+        want4 = want4 + hops4[k]
+    assert torch.equal(out4, want4 / (K + 1))
+    _, out5 = op.propagate_fused(xd, K, mode="fast", keep="none", agg="weighted", start=1, end=K, fuse_norm=False,
+                                 weights=[0.0, 0.5, 0.25, 2.0, 0.0])
+    want5 = hops4[1] * 0.5
+    want5 = want5 + hops4[2] * 0.25
+    want5 = want5 + hops4[3] * 2.0
+    assert torch.equal(out5, want5)
     hops5, _ = op.propagate_fused(xd, K, mode="exact", keep="all")
     assert np.array_equal(hops5[K].cpu().numpy(), ref[K])
     op.close()
