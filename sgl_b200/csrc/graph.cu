@@ -5,6 +5,7 @@
 // nnz-balanced warp schedule is computed once, and K hops reuse both.
 #include <stdarg.h>
 #include <stdio.h>
+#include <stdlib.h>
 #include <string.h>
 
 #include <algorithm>
@@ -415,6 +416,12 @@ int sglb200_graph_create(sglb200_graph_t *out, int64_t n_rows, int64_t n_cols, i
         int64_t ti = ((per_warp + 31) / 32) * 32;
         if (ti < 32) ti = 32;
         if (ti > 256) ti = 256;
+        // graphs that fill the chip many times over: longer tiles amortise the tile start-up (descriptor, first stream
+        // batch, first row-end window).  Measured per hop (profiles/r02_tile_items.txt): products-shape 5.32 / 5.04 / 4.87 ms
+        // at 256 / 512 / 1024 items, rmat22 3.50 / 3.36 ms at 256 / 512, products d=16 1.18 / 1.04 / 0.99 ms at 128 / 256 / 512
+        const char *cap = getenv("SGLB200_TILE_ITEMS_MAX");
+        const int64_t max_items = cap ? atoll(cap) : 1024;
+        while (ti < max_items && per_warp >= 8 * ti) ti *= 2;
         g->tile_items = (int)ti;
     }
     g->split_threshold = split_threshold > 0 ? split_threshold : 64;  // rows above 64 non-zeros may be cut
