@@ -68,6 +68,10 @@ struct sglb200_graph {
     int32_t *idx_tag = nullptr; // nnz (+ kStreamPad): column id | bit 31 "last non-zero of its row" -- the stream the TMA hop
                                 // kernel walks (spmm_tma.cu); valid when empty_rows == 0
     int64_t empty_rows = -1;    // rows without any non-zero (-1: not counted yet)
+    int2 *pairs = nullptr;      // nnz (+ kStreamPad): (idx_tag[j], bits of vals[j]) interleaved -- ONE 8-byte load per non-zero
+                                // for the lane-group kernel, whose 32/G groups each read their own stream (separate 4-byte
+                                // arrays cost it as many L1 wavefronts as the feature gathers themselves)
+    bool pairs_valid = false;   // false after the values were rewritten
     int tile_items = 0;
     int split_threshold = 0;
     sglb200::Schedule fast, exact;
@@ -95,6 +99,7 @@ struct sglb200_graph {
 namespace sglb200 {
 constexpr int64_t kStreamPad = 128;  // zeroed elements behind indices / values: bulk copies of the last chunk stay in bounds
 int build_stream_tags(sglb200_graph *g, cudaStream_t stream);
+int build_stream_pairs(sglb200_graph *g, cudaStream_t stream);
 int build_schedule(sglb200_graph *g, Schedule *s, int64_t split_threshold, cudaStream_t stream);
 void free_schedule(Schedule *s);
 int ensure_carry_ws(sglb200_graph *g, size_t floats, cudaStream_t stream);

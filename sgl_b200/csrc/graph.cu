@@ -274,6 +274,32 @@ int build_stream_tags(sglb200_graph *g, cudaStream_t stream)
     return SGLB200_OK;
 }
 
+__global__ void interleave_pairs_kernel(const int32_t *__restrict__ idx_tag, const float *__restrict__ vals, int64_t count,
+                                        int2 *__restrict__ pairs)
+{
+    for (int64_t j = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; j < count; j += (int64_t)gridDim.x * blockDim.x)
+        pairs[j] = make_int2(idx_tag[j], __float_as_int(vals[j]));
+}
+
+int build_stream_pairs(sglb200_graph *g, cudaStream_t stream)
+{
+    if (!g->idx_tag || g->nnz == 0) return SGLB200_OK;
+    if (!g->pairs) {
+        SGL_CUDA_CHECK(cudaMalloc(&g->pairs, sizeof(int2) * (g->nnz + kStreamPad)));
+        g->bytes_resident += sizeof(int2) * (size_t)(g->nnz + kStreamPad);
+        g->pairs_valid = false;
+    }
+    if (!g->pairs_valid) {
+        const int64_t count = g->nnz + kStreamPad;   // the padding of both arrays is zero
+        int64_t blocks = (count + 255) / 256;
+        if (blocks > 148 * 32) blocks = 148 * 32;
+        interleave_pairs_kernel<<<(unsigned)blocks, 256, 0, stream>>>(g->idx_tag, g->vals, count, g->pairs);
+        SGL_CUDA_CHECK(cudaGetLastError());
+        g->pairs_valid = true;
+    }
+    return SGLB200_OK;
+}
+
 __global__ void widen_indptr_kernel(const int32_t *__restrict__ in, int64_t *__restrict__ out, int64_t n)
 {
     const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
@@ -484,6 +510,7 @@ int sglb200_graph_destroy(sglb200_graph_t g)
     cudaFree(g->indices);
     cudaFree(g->vals);
     cudaFree(g->idx_tag);
+    cudaFree(g->pairs);
     cudaFree(g->raw_w);
     cudaFree(g->row_scale);
     cudaFree(g->col_scale);
@@ -508,6 +535,7 @@ int sglb200_graph_set_values(sglb200_graph_t g, const float *vals, int loc, void
     clear_error();
     SGL_REQUIRE(g && vals, "graph_set_values: NULL argument");
     if (g->nnz == 0) return SGLB200_OK;
+    g->pairs_valid = false;
     SGL_CUDA_CHECK(cudaMemcpyAsync(g->vals, vals, sizeof(float) * g->nnz,
                                    loc == SGLB200_HOST ? cudaMemcpyHostToDevice : cudaMemcpyDeviceToDevice,
                                    (cudaStream_t)stream));
@@ -560,6 +588,7 @@ int sglb200_normalize_values(sglb200_graph_t g, const double *raw_w, const doubl
     clear_error();
     SGL_REQUIRE(g && raw_w && d_left && d_right, "normalize_values: NULL argument");
     SGL_REQUIRE(g->n_rows == g->n_cols, "normalize_values: operator must be square");
+    g->pairs_valid = false;
     cudaStream_t stream = (cudaStream_t)stream_;
     const double *w = raw_w, *dl = d_left, *dr = d_right;
     double *tmp = nullptr;

@@ -152,15 +152,23 @@ __global__ void __launch_bounds__(kLwWarps * 32)
 __global__ void __launch_bounds__(kLwWarps * 32)
     lw_back_score_kernel(int kind, LwPtrs feats, LwGradPtrs grads, int n_all, int start, int kp, int64_t B, int d,
                          const float *__restrict__ w, const float *__restrict__ dscore, float *__restrict__ grad_w,
-                         float *__restrict__ grad_bias, int len_w)
+                         float *__restrict__ grad_bias, int len_w, int private_rows)
 {
-    extern __shared__ float s_gw[];  // len_w + 1
-    for (int c = threadIdx.x; c <= len_w; c += blockDim.x) s_gw[c] = 0.0f;
+    // parameter-gradient partials: one PRIVATE accumulator row per warp when they fit in shared memory (`private_rows`):
+    // lane c owns columns c, c+32, ... of its warp's row, so the node loop needs no atomics at all (the round-1 form did a
+    // shared-memory atomicAdd per element, node and hop, 8 warps contending on the same addresses: 1.2 TB/s); the rows
+    // are summed once at the end.  Otherwise all warps share one row through atomics.
+    extern __shared__ float s_gw[];  // rows x (len_w + 1)
+    const int rows = private_rows ? kLwWarps : 1;
+    const int row_len = len_w + 1;
+    for (int c = threadIdx.x; c < rows * row_len; c += blockDim.x) s_gw[c] = 0.0f;
     __syncthreads();
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int ref_hops = kind == 3 ? 1 : (kind == 4 ? n_all : 0);
     const float *w_hop = w + (size_t)ref_hops * d;
-    float *s_hop = s_gw + (size_t)ref_hops * d;
+    float *my = s_gw + (size_t)(private_rows ? warp : 0) * row_len;
+    float *s_hop = my + (size_t)ref_hops * d;
+    float dr_total = 0.0f;
     for (int64_t n = (int64_t)blockIdx.x * kLwWarps + warp; n < B; n += (int64_t)gridDim.x * kLwWarps) {
         float dr = 0.0f;
         for (int h = 0; h < kp; ++h) {
@@ -170,23 +178,30 @@ __global__ void __launch_bounds__(kLwWarps * 32)
             float *gy = grads.g[start + h];
             for (int c = lane; c < d; c += 32) {
                 if (gy) gy[n * d + c] += ds * w_hop[c];
-                atomicAdd(&s_hop[c], ds * y[c]);
+                if (private_rows) s_hop[c] = fmaf(ds, y[c], s_hop[c]);
+                else atomicAdd(&s_hop[c], ds * y[c]);
             }
         }
-        if (lane == 0) atomicAdd(&s_gw[len_w], dr);
+        dr_total += dr;
         for (int k = 0; k < ref_hops; ++k) {
             const float *x = feats.f[k] + n * d;
             float *gx = grads.g[k];
             const float *wk = w + (size_t)k * d;
             for (int c = lane; c < d; c += 32) {
                 if (gx) gx[n * d + c] += dr * wk[c];
-                atomicAdd(&s_gw[(size_t)k * d + c], dr * x[c]);
+                if (private_rows) my[(size_t)k * d + c] = fmaf(dr, x[c], my[(size_t)k * d + c]);
+                else atomicAdd(&my[(size_t)k * d + c], dr * x[c]);
             }
         }
     }
+    if (lane == 0) atomicAdd(&my[len_w], dr_total);
     __syncthreads();
-    for (int c = threadIdx.x; c < len_w; c += blockDim.x) atomicAdd(&grad_w[c], s_gw[c]);
-    if (threadIdx.x == 0) atomicAdd(grad_bias, s_gw[len_w]);
+    for (int c = threadIdx.x; c < row_len; c += blockDim.x) {
+        float t = 0.0f;
+        for (int r = 0; r < rows; ++r) t += s_gw[(size_t)r * row_len + c];
+        if (c < len_w) atomicAdd(&grad_w[c], t);
+        else atomicAdd(grad_bias, t);
+    }
 }
 
 static int lw_check(const char *who, int kind, const float *const *feats, int n_all, int start, int end, int64_t B, int d)
@@ -256,12 +271,13 @@ int sglb200_lw_backward(int kind, const float *const *feats, int n_all, int star
     const unsigned blocks = (unsigned)((B + kLwWarps - 1) / kLwWarps);
     lw_back_node_kernel<<<blocks, kLwWarps * 32, 0, stream>>>(kind, f, g, start, kp, B, d, scores, hop_w, grad_out, scratch);
     SGL_CUDA_CHECK(cudaGetLastError());
-    const size_t smem = (size_t)(len_w + 1) * sizeof(float);
+    const int private_rows = (size_t)kLwWarps * (len_w + 1) * sizeof(float) <= 96 * 1024 ? 1 : 0;
+    const size_t smem = (size_t)(private_rows ? kLwWarps : 1) * (len_w + 1) * sizeof(float);
     if (smem > 48 * 1024)
         SGL_CUDA_CHECK(cudaFuncSetAttribute(lw_back_score_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     const unsigned blocks2 = blocks < 148u * 4u ? blocks : 148u * 4u;
     lw_back_score_kernel<<<blocks2, kLwWarps * 32, smem, stream>>>(kind, f, g, n_all, start, kp, B, d, w, scratch, grad_w,
-                                                                   grad_bias, len_w);
+                                                                   grad_bias, len_w, private_rows);
     SGL_CUDA_CHECK(cudaGetLastError());
     return SGLB200_OK;
 }

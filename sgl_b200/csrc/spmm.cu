@@ -691,7 +691,7 @@ static void pick_shape(int d, int max_vec, int *vec_out, int *vpl_out, int *col_
 
 int spmm_launch_tiles(sglb200_graph *g, const float *X, int64_t ldx, float *Y, int64_t ldy, int d, int mode,
                       int accumulate, int64_t tile_begin, int64_t tile_end, cudaStream_t stream);
-cudaError_t spmm_group_launch(const SpmmParams &p, bool accum, const int32_t *idx_tag, cudaStream_t stream);  // spmm_group.cu
+cudaError_t spmm_group_launch(const SpmmParams &p, bool accum, const int32_t *idx_tag, const int2 *pairs, cudaStream_t stream);  // spmm_group.cu
 bool spmm_tma_eligible(const sglb200_graph *g, const float *X, int64_t ldx, int d);      // spmm_tma.cu
 cudaError_t spmm_tma_launch(const sglb200_graph *g, const SpmmParams &p, cudaStream_t stream);
 
@@ -920,7 +920,14 @@ int spmm_launch_ex(sglb200_graph *g, const float *X, int64_t ldx, float *Y, int6
         e = spmm_tma_launch(g, p, stream);
     }
     else if (use_groups) {
-        e = spmm_group_launch(p, acc, tags, stream);
+        // the interleaved (flagged column, value) stream of the normalised values: one 8-byte load per non-zero
+        const int2 *pairs = nullptr;
+        if (tags && !acc && !p.epi.active && p.vals == g->vals && env_int("SGLB200_GROUP_PAIRS", 1) != 0) {
+            const int st = build_stream_pairs(g, stream);
+            if (st != SGLB200_OK) return st;
+            pairs = g->pairs;
+        }
+        e = spmm_group_launch(p, acc, tags, pairs, stream);
     }
     else if (vec == 4 && vpl == 1) {
         switch (variant) {

@@ -21,10 +21,15 @@ namespace sglb200 {
 // COOP (with FLAG): the (col, val) stream of ALL groups of a warp is fetched by the whole warp -- one coalesced load per
 // group and batch (1-2 cache lines) instead of every group reading 16 bytes of its own stream per instruction (8 lines):
 // the L1 tag stage was the busiest unit of the narrow-row hop (61 %), and a quarter of its work was this stream.
-template <int G, int U, bool ACCUM, bool EPI = false, bool FLAG = false, int MINB = 3, bool COOP = false>
-__global__ void __launch_bounds__(kWarpsPerBlock * 32, MINB) spmm_group_kernel(const __grid_constant__ SpmmParams p, const int32_t *__restrict__ idx_tag)
+// PAIRS (with FLAG): (flagged column, value) come interleaved from ONE array: one 8-byte load per non-zero.  ncu on the
+// separate-array form (products-shape, d=16): L1 data pipe 70 % busy, and the two 4-byte streams -- 8 cache lines touched
+// per instruction for 128 useful bytes -- cost as many wavefronts as the gathers.
+template <int G, int U, bool ACCUM, bool EPI = false, bool FLAG = false, int MINB = 3, bool COOP = false, bool PAIRS = false>
+__global__ void __launch_bounds__(kWarpsPerBlock * 32, MINB) spmm_group_kernel(const __grid_constant__ SpmmParams p, const int32_t *__restrict__ idx_tag,
+                                                                            const int2 *__restrict__ pair_stream)
 {
     static_assert(!COOP || FLAG, "the cooperative fetch walks the flagged stream");
+    static_assert(!PAIRS || (FLAG && !COOP), "the pair stream is the flagged one");
     static_assert(!(FLAG && ACCUM), "the flagged walk starts every chain from zero");
     static_assert(!(EPI && ACCUM), "the fused row flush starts every chain from zero");
     constexpr int NG = 32 / G;             // tiles per warp
@@ -190,8 +195,14 @@ __global__ void __launch_bounds__(kWarpsPerBlock * 32, MINB) spmm_group_kernel(c
                 col_next[i] = 0;
                 val_next[i] = 0.0f;
                 if (nb < n_nnz) {
-                    col_next[i] = __ldg(cols + nb);
-                    val_next[i] = p.vals ? __ldg(vals + nb) : 1.0f;
+                    if constexpr (PAIRS) {
+                        const int2 pr = __ldg(pair_stream + j0 + nb);
+                        col_next[i] = pr.x;
+                        val_next[i] = __int_as_float(pr.y);
+                    } else {
+                        col_next[i] = __ldg(cols + nb);
+                        val_next[i] = p.vals ? __ldg(vals + nb) : 1.0f;
+                    }
                 }
             }
         }
@@ -321,33 +332,34 @@ __global__ void __launch_bounds__(kWarpsPerBlock * 32, MINB) spmm_group_kernel(c
 }
 
 template <int G, int U>
-static cudaError_t launch_group(const SpmmParams &p, bool accum, const int32_t *idx_tag, cudaStream_t stream)
+static cudaError_t launch_group(const SpmmParams &p, bool accum, const int32_t *idx_tag, const int2 *pairs, cudaStream_t stream)
 {
     constexpr int NG = 32 / G;
     const int64_t tiles = p.n_tiles - p.tile_begin;
     const unsigned blocks = (unsigned)((tiles + (int64_t)kWarpsPerBlock * NG - 1) / ((int64_t)kWarpsPerBlock * NG));
     static const char *coop_env = getenv("SGLB200_GROUP_COOP");
     const bool coop = coop_env && atoi(coop_env) == 1;   // measured and rejected as default: d=16 1139 vs 1044 us (products), 799 vs 728 (rmat22)
-    if (accum) spmm_group_kernel<G, U, true><<<blocks, kWarpsPerBlock * 32, 0, stream>>>(p, nullptr);
-    else if (p.epi.active && idx_tag) spmm_group_kernel<G, U, false, true, true><<<blocks, kWarpsPerBlock * 32, 0, stream>>>(p, idx_tag);
-    else if (idx_tag && U == 8 && coop) spmm_group_kernel<G, U, false, false, true, 3, true><<<blocks, kWarpsPerBlock * 32, 0, stream>>>(p, idx_tag);
-    else if (p.epi.active) spmm_group_kernel<G, U, false, true><<<blocks, kWarpsPerBlock * 32, 0, stream>>>(p, nullptr);
-    else if (idx_tag && U == 4) spmm_group_kernel<G, U, false, false, true, 4><<<blocks, kWarpsPerBlock * 32, 0, stream>>>(p, idx_tag);
-    else if (idx_tag) spmm_group_kernel<G, U, false, false, true><<<blocks, kWarpsPerBlock * 32, 0, stream>>>(p, idx_tag);
-    else spmm_group_kernel<G, U, false><<<blocks, kWarpsPerBlock * 32, 0, stream>>>(p, nullptr);
+    if (accum) spmm_group_kernel<G, U, true><<<blocks, kWarpsPerBlock * 32, 0, stream>>>(p, nullptr, nullptr);
+    else if (p.epi.active && idx_tag) spmm_group_kernel<G, U, false, true, true><<<blocks, kWarpsPerBlock * 32, 0, stream>>>(p, idx_tag, nullptr);
+    else if (idx_tag && U == 8 && coop) spmm_group_kernel<G, U, false, false, true, 3, true><<<blocks, kWarpsPerBlock * 32, 0, stream>>>(p, idx_tag, nullptr);
+    else if (p.epi.active) spmm_group_kernel<G, U, false, true><<<blocks, kWarpsPerBlock * 32, 0, stream>>>(p, nullptr, nullptr);
+    else if (idx_tag && U == 4) spmm_group_kernel<G, U, false, false, true, 4><<<blocks, kWarpsPerBlock * 32, 0, stream>>>(p, idx_tag, nullptr);
+    else if (idx_tag && pairs) spmm_group_kernel<G, U, false, false, true, 3, false, true><<<blocks, kWarpsPerBlock * 32, 0, stream>>>(p, idx_tag, pairs);
+    else if (idx_tag) spmm_group_kernel<G, U, false, false, true><<<blocks, kWarpsPerBlock * 32, 0, stream>>>(p, idx_tag, nullptr);
+    else spmm_group_kernel<G, U, false><<<blocks, kWarpsPerBlock * 32, 0, stream>>>(p, nullptr, nullptr);
     return cudaGetLastError();
 }
 
 // d <= 64, float4 rows: picks the narrowest group that holds a row
 // idx_tag: the flagged column stream (NULL: walk with row-pointer windows -- graphs with empty rows, accumulate)
-cudaError_t spmm_group_launch(const SpmmParams &p, bool accum, const int32_t *idx_tag, cudaStream_t stream)
+cudaError_t spmm_group_launch(const SpmmParams &p, bool accum, const int32_t *idx_tag, const int2 *pairs, cudaStream_t stream)
 {
     const int slices = (p.d + 3) / 4;
     static const char *u_env = getenv("SGLB200_GROUP_U");
     const bool u4 = u_env && atoi(u_env) == 4 && !accum && !p.epi.active && idx_tag;   // experiment: 4 rows in flight, 32 warps / SM
-    if (slices <= 4) return u4 ? launch_group<4, 4>(p, accum, idx_tag, stream) : launch_group<4, 8>(p, accum, idx_tag, stream);
-    if (slices <= 8) return u4 ? launch_group<8, 4>(p, accum, idx_tag, stream) : launch_group<8, 8>(p, accum, idx_tag, stream);
-    return u4 ? launch_group<16, 4>(p, accum, idx_tag, stream) : launch_group<16, 8>(p, accum, idx_tag, stream);
+    if (slices <= 4) return u4 ? launch_group<4, 4>(p, accum, idx_tag, pairs, stream) : launch_group<4, 8>(p, accum, idx_tag, pairs, stream);
+    if (slices <= 8) return u4 ? launch_group<8, 4>(p, accum, idx_tag, pairs, stream) : launch_group<8, 8>(p, accum, idx_tag, pairs, stream);
+    return u4 ? launch_group<16, 4>(p, accum, idx_tag, pairs, stream) : launch_group<16, 8>(p, accum, idx_tag, pairs, stream);
 }
 
 }  // namespace sglb200
