@@ -519,7 +519,13 @@ def run_b200(args):
                 "algorithmic_bytes_per_launch_fused": algorithmic_bytes_per_hop_fused(n, nnz, d),
                 "gather_bytes_per_launch": nnz * (8 + 4 * d) + n * (8 + 4 * d), "us_per_launch": hop_s * 1e6,
                 "dram_measured_frac": (traffic / hop_s / 1e9 / peak_gbs) if traffic else None,
-                "peak_source": peak_src}
+                "peak_source": peak_src,
+                # what actually bounds a gather formulation on an input without locality: every non-zero moves one feature
+                # row L2 -> SM; ceiling = random row gather measured on this GPU (profiles/r02_gather4_microbench.txt: 18.6 TB/s
+                # for L2-resident rows with LDG.128 or TMA gather4, 7.5 TB/s from HBM)
+                "gather_path": {"achieved": (nnz * (8 + 4 * d) + n * (8 + 4 * d)) / hop_s / 1e9, "peak": 18600.0, "unit": "GB/s",
+                                "frac": (nnz * (8 + 4 * d) + n * (8 + 4 * d)) / hop_s / 1e9 / 18600.0,
+                                "peak_source": "measured L2->SM random 512-byte row gather, profiles/r02_gather4_microbench.txt"}}
 
     # ---- parity spot check on the timed buffers: every hop against the oracle on a row sample -------------------
     rng = np.random.default_rng(1)

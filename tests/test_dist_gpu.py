@@ -68,3 +68,52 @@ def test_two_rank_nccl_row_partition(tmp_path, mode, chunks, transport):
     for r in range(2):
         got = np.load(tmp_path / f"{mode}_{r}.npy")
         assert np.array_equal(got, ref[:, bounds[r]:bounds[r + 1]])       # exact mode: bit-identical to one GPU
+
+
+def _feature_worker(rank, world, port, tmp):
+    import scipy.sparse as sp
+    import torch.distributed as dist
+    from sgl_b200.dist import FeatureSplitOperator
+    os.environ["MASTER_ADDR"], os.environ["MASTER_PORT"] = "127.0.0.1", str(port)
+    torch.cuda.set_device(rank)
+    dist.init_process_group("nccl", rank=rank, world_size=world, device_id=torch.device("cuda", rank))
+    try:
+        rng = np.random.default_rng(6)
+        n, d, K = 12000, 100, 3
+        rows = rng.integers(0, n, 90000)
+        cols = (rng.zipf(1.25, rows.size) - 1) % n
+        adj = sp.csr_matrix((np.ones(2 * rows.size, dtype=np.float32),
+                             (np.concatenate([rows, cols]), np.concatenate([cols, rows]))), shape=(n, n))
+        a = O.laplacian_adj(adj, 0.5)
+        x = rng.standard_normal((n, d)).astype(np.float32)
+        import scipy.sparse
+        fs = FeatureSplitOperator(adj_norm=scipy.sparse.csr_matrix((a.data, a.indices, a.indptr), shape=a.shape), world=world,
+                                  rank=rank, mode="exact")
+        cb = fs.column_bounds(d, world)
+        blk = torch.from_numpy(np.ascontiguousarray(x[:, cb[rank]:cb[rank + 1]])).cuda()
+        hops = fs.propagate(blk, K)                       # lane-group kernel on the column block, no exchange
+        shard = fs.rows_from_columns(hops[-1], d)         # the one all-to-all: this rank's rows, all columns
+        np.save(os.path.join(tmp, f"fs_rows_{rank}.npy"), shard.cpu().numpy())
+        if rank == 0:
+            np.save(os.path.join(tmp, "fs_ref.npy"), O.propagate(a, x, K, "fma")[-1])
+        fs.close()
+    finally:
+        dist.destroy_process_group()
+
+
+def test_two_rank_feature_split_is_bit_identical_to_one_gpu(tmp_path):
+    """Default multi-GPU partition: A^ replicated, feature columns split, rows_from_columns over NCCL; EXACT mode equals the
+    oracle's single-GPU chain bit for bit on every rank's row shard."""
+    if not torch.cuda.is_available() or torch.cuda.device_count() < 2:
+        pytest.skip("needs 2 GPUs")
+    import torch.multiprocessing as mp
+    from sgl_b200.dist import FeatureSplitOperator
+    s = socket.socket()
+    s.bind(("127.0.0.1", 0))
+    port = s.getsockname()[1]
+    s.close()
+    mp.spawn(_feature_worker, args=(2, port, str(tmp_path)), nprocs=2, join=True)
+    ref = np.load(tmp_path / "fs_ref.npy")
+    rb = FeatureSplitOperator.row_bounds(ref.shape[0], 2)
+    for r in range(2):
+        assert np.array_equal(np.load(tmp_path / f"fs_rows_{r}.npy"), ref[rb[r]:rb[r + 1]])
