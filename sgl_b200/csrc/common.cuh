@@ -67,6 +67,9 @@ struct sglb200_graph {
     float *vals = nullptr;      // nnz (+ kStreamPad), device
     int32_t *idx_tag = nullptr; // nnz (+ kStreamPad): column id | bit 31 "last non-zero of its row" -- the stream the TMA hop
                                 // kernel walks (spmm_tma.cu); valid when empty_rows == 0
+    int32_t *idx_cold = nullptr;   // nnz (+ kStreamPad): column id | bit 30 "rarely referenced column" (build_cold_tags)
+    int64_t cold_hub_rows = -1;    // the hub budget idx_cold was built for
+    int cold_threshold = 0;        // reference count from which a column is a hub
     int64_t empty_rows = -1;    // rows without any non-zero (-1: not counted yet)
     int2 *pairs = nullptr;      // nnz (+ kStreamPad): (idx_tag[j], bits of vals[j]) interleaved -- ONE 8-byte load per non-zero
                                 // for the lane-group kernel, whose 32/G groups each read their own stream (separate 4-byte
@@ -99,6 +102,7 @@ struct sglb200_graph {
 namespace sglb200 {
 constexpr int64_t kStreamPad = 128;  // zeroed elements behind indices / values: bulk copies of the last chunk stay in bounds
 int build_stream_tags(sglb200_graph *g, cudaStream_t stream);
+int build_cold_tags(sglb200_graph *g, int64_t hub_rows, cudaStream_t stream);
 int build_stream_pairs(sglb200_graph *g, cudaStream_t stream);
 int build_schedule(sglb200_graph *g, Schedule *s, int64_t split_threshold, cudaStream_t stream);
 void free_schedule(Schedule *s);

@@ -266,11 +266,85 @@ int build_stream_tags(sglb200_graph *g, cudaStream_t stream)
     cudaFree(cnt);
     if (e != cudaSuccess) {
         cudaFree(g->idx_tag);
+    cudaFree(g->idx_cold);
         g->idx_tag = nullptr;
         SGL_CUDA_CHECK(e);
     }
     g->empty_rows = (int64_t)h;
     g->bytes_resident += sizeof(int32_t) * (size_t)(g->nnz + kStreamPad);
+    return SGLB200_OK;
+}
+
+// ---- cold-column tags (experiment: SGLB200_COLD_HINT) ---------------------------------------------------------------
+// idx_cold[j] = indices[j] | (1<<30 if column indices[j] is referenced fewer times than the hub threshold).  The hop
+// kernel loads rows of cold columns with an L2 evict_first policy so that they do not push the few heavily re-read
+// rows out of L2.  The threshold is the smallest reference count such that at most `hub_rows` columns reach it.
+__global__ void count_cols_kernel(const int32_t *__restrict__ indices, int64_t nnz, int32_t *__restrict__ counts)
+{
+    for (int64_t j = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; j < nnz; j += (int64_t)gridDim.x * blockDim.x)
+        atomicAdd(&counts[indices[j]], 1);
+}
+
+constexpr int kCountBuckets = 4096;
+
+__global__ void count_hist_kernel(const int32_t *__restrict__ counts, int64_t n_cols, unsigned long long *__restrict__ hist)
+{
+    for (int64_t c = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; c < n_cols; c += (int64_t)gridDim.x * blockDim.x) {
+        const int k = counts[c] < kCountBuckets - 1 ? counts[c] : kCountBuckets - 1;
+        atomicAdd(&hist[k], 1ULL);
+    }
+}
+
+__global__ void tag_cold_kernel(const int32_t *__restrict__ indices, int64_t nnz, const int32_t *__restrict__ counts,
+                                int threshold, int32_t *__restrict__ out)
+{
+    for (int64_t j = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; j < nnz; j += (int64_t)gridDim.x * blockDim.x) {
+        const int32_t c = indices[j];
+        out[j] = counts[c] < threshold ? (c | 0x40000000) : c;
+    }
+}
+
+int build_cold_tags(sglb200_graph *g, int64_t hub_rows, cudaStream_t stream)
+{
+    if (g->nnz == 0 || g->n_cols >= (1LL << 30)) return SGLB200_OK;
+    if (g->idx_cold && g->cold_hub_rows == hub_rows) return SGLB200_OK;
+    int32_t *counts = nullptr;
+    unsigned long long *hist = nullptr;
+    SGL_CUDA_CHECK(cudaMalloc(&counts, sizeof(int32_t) * g->n_cols));
+    cudaError_t e = cudaMalloc(&hist, sizeof(unsigned long long) * kCountBuckets);
+    if (e == cudaSuccess && !g->idx_cold) {
+        e = cudaMalloc(&g->idx_cold, sizeof(int32_t) * (g->nnz + kStreamPad));
+        if (e == cudaSuccess) {
+            g->bytes_resident += sizeof(int32_t) * (size_t)(g->nnz + kStreamPad);
+            e = cudaMemsetAsync(g->idx_cold + g->nnz, 0, sizeof(int32_t) * kStreamPad, stream);
+        }
+    }
+    if (e == cudaSuccess) e = cudaMemsetAsync(counts, 0, sizeof(int32_t) * g->n_cols, stream);
+    if (e == cudaSuccess) e = cudaMemsetAsync(hist, 0, sizeof(unsigned long long) * kCountBuckets, stream);
+    std::vector<unsigned long long> h(kCountBuckets);
+    if (e == cudaSuccess) {
+        count_cols_kernel<<<148 * 16, 256, 0, stream>>>(g->indices, g->nnz, counts);
+        count_hist_kernel<<<148 * 8, 256, 0, stream>>>(counts, g->n_cols, hist);
+        e = cudaMemcpyAsync(h.data(), hist, sizeof(unsigned long long) * kCountBuckets, cudaMemcpyDeviceToHost, stream);
+    }
+    if (e == cudaSuccess) e = cudaStreamSynchronize(stream);
+    int threshold = kCountBuckets;       // nothing is a hub
+    if (e == cudaSuccess) {
+        unsigned long long above = 0;
+        for (int k = kCountBuckets - 1; k >= 1; --k) {
+            if (above + h[k] > (unsigned long long)hub_rows) break;
+            above += h[k];
+            threshold = k;
+        }
+        tag_cold_kernel<<<148 * 16, 256, 0, stream>>>(g->indices, g->nnz, counts, threshold, g->idx_cold);
+        e = cudaGetLastError();
+        if (e == cudaSuccess) e = cudaStreamSynchronize(stream);
+    }
+    cudaFree(counts);
+    cudaFree(hist);
+    SGL_CUDA_CHECK(e);
+    g->cold_hub_rows = hub_rows;
+    g->cold_threshold = threshold;
     return SGLB200_OK;
 }
 

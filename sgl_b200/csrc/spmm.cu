@@ -170,7 +170,7 @@ __global__ void __launch_bounds__(kWarpsPerBlock * 32, MINB) spmm_flat_kernel(co
         if (row < row_end && p.indptr[row + 1] == j0) flush_row();
     }
 
-    const int32_t *cols = (FLAG ? idx_tag : p.indices) + j0;
+    const int32_t *cols = (FLAG || (HINT && idx_tag != nullptr) ? idx_tag : p.indices) + j0;
     const float *vals = p.vals + j0;
     uint64_t pol_hub = 0, pol_cold = 0;
     if constexpr (HINT) {
@@ -179,6 +179,7 @@ __global__ void __launch_bounds__(kWarpsPerBlock * 32, MINB) spmm_flat_kernel(co
         else asm volatile("createpolicy.fractional.L2::evict_normal.b64 %0, 1.0;" : "=l"(pol_cold));
     }
     const uint32_t hub_cols = p.hub_cols;
+    const bool cold_tags = HINT && idx_tag != nullptr;
 
     // (col, val) of the next 32 non-zeros are fetched into registers one batch ahead of their publication
     int32_t col_next = 0;
@@ -210,11 +211,22 @@ __global__ void __launch_bounds__(kWarpsPerBlock * 32, MINB) spmm_flat_kernel(co
         const int2 *pp = pairs + (pos & 63);
 #pragma unroll
         for (int u = 0; u < U; ++u) {
-            const uint32_t c = (uint32_t)pp[u].x & (FLAG ? 0x3fffffffu : 0xffffffffu);
+            const uint32_t raw = (uint32_t)pp[u].x;
+            const uint32_t c = raw & (FLAG || HINT ? 0x3fffffffu : 0xffffffffu);
             if constexpr (HINT) {
-                const uint64_t pol = c < hub_cols ? pol_hub : pol_cold;
+                if (cold_tags) {   // bit 30 marks a rarely referenced column: evict_first, hubs load normally (warp-uniform)
+                    if (raw & 0x40000000u) {
 #pragma unroll
-                for (int v = 0; v < VPL; ++v) buf[u][v].load_hint(xbase[v] + (uint64_t)c * ldx_bytes, pol);
+                        for (int v = 0; v < VPL; ++v) buf[u][v].load_hint(xbase[v] + (uint64_t)c * ldx_bytes, pol_cold);
+                    } else {
+#pragma unroll
+                        for (int v = 0; v < VPL; ++v) buf[u][v].load_nc(xbase[v] + (uint64_t)c * ldx_bytes);
+                    }
+                } else {
+                    const uint64_t pol = c < hub_cols ? pol_hub : pol_cold;
+#pragma unroll
+                    for (int v = 0; v < VPL; ++v) buf[u][v].load_hint(xbase[v] + (uint64_t)c * ldx_bytes, pol);
+                }
             } else {
 #pragma unroll
                 for (int v = 0; v < VPL; ++v) buf[u][v].load_nc(xbase[v] + (uint64_t)c * ldx_bytes);
@@ -618,6 +630,7 @@ static cudaError_t launch_windowed(Kern kern, const SpmmParams &p, dim3 grid, cu
     return cudaLaunchKernelEx(&cfg, kern, p, (const int32_t *)nullptr);
 }
 
+static const int32_t *g_cold_tags = nullptr;   // likewise: the cold-tagged column stream (SGLB200_COLD_HINT)
 static const int32_t *g_flat_tags = nullptr;   // set by spmm_launch_ex for the duration of one launch (host, single thread per handle)
 
 template <int VEC, int VPL, int U, int MINB, int PIPE = 1>
@@ -640,8 +653,8 @@ static cudaError_t launch_flat(const SpmmParams &p, bool accum, dim3 grid, cudaS
         else spmm_flat_kernel<VEC, VPL, U, false, MINB, 1, false, false, true><<<grid, kWarpsPerBlock * 32, 0, stream>>>(p, tags);
         return cudaGetLastError();
     }
-    if (!accum && p.hub_cols > 0) {
-        spmm_flat_kernel<VEC, VPL, U, false, MINB, PIPE, true><<<grid, kWarpsPerBlock * 32, 0, stream>>>(p, nullptr);
+    if (!accum && (p.hub_cols > 0 || g_cold_tags)) {
+        spmm_flat_kernel<VEC, VPL, U, false, MINB, PIPE, true><<<grid, kWarpsPerBlock * 32, 0, stream>>>(p, g_cold_tags);
         return cudaGetLastError();
     }
     if (!accum) return launch_windowed(spmm_flat_kernel<VEC, VPL, U, false, MINB, PIPE>, p, grid, stream);
@@ -884,6 +897,15 @@ int spmm_launch_ex(sglb200_graph *g, const float *X, int64_t ldx, float *Y, int6
     // the warp kernel keeps its row-pointer windows by default: its check-free groups beat the per-non-zero flag test
     // (measured: arxiv 101 vs 111 us, products 5.3 vs 6.0 ms per hop); the lane-group and TMA kernels use the flags
     g_flat_tags = env_int("SGLB200_FLAT_FLAGS", 0) != 0 ? tags : nullptr;
+    g_cold_tags = nullptr;
+    if (!acc && !(epi && epi->active) && !p.red_agg && env_int("SGLB200_COLD_HINT", 0) != 0 && g->n_cols < (1LL << 30)) {
+        // hub budget: the rows of X that should own L2 (default 48 MB of the 126 MB)
+        const int64_t hub_rows = ((int64_t)env_int("SGLB200_HUB_MB", 48) << 20) / ((int64_t)ldx * 4);
+        const int st = build_cold_tags(g, hub_rows, stream);
+        if (st != SGLB200_OK) return st;
+        g_cold_tags = g->idx_cold;
+        p.cold_policy = env_int("SGLB200_COLD_POLICY", 1);
+    }
     cudaError_t e = cudaSuccess;
 #define SGL_SHAPE(V, L, UU, MB) \
     if (vec == V && vpl == L) e = launch_flat<V, L, UU, MB>(p, acc, grid, stream)
