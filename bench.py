@@ -64,6 +64,7 @@ def parse_args():
                     help="experiment: relabel the vertices by descending degree before building A^")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--no-pad", action="store_true", help="feature split: dense row stride for narrow column blocks")
     ap.add_argument("--no-comparators", action="store_true")
     ap.add_argument("--traffic", default="ncu", choices=["ncu", "file", "none"],
                     help="roofline.traffic: measured by an ncu child process in this run (default), read from "
@@ -769,9 +770,12 @@ def run_feature_split(args):
     else:
         x_full = torch.randn(n, d, generator=torch.Generator().manual_seed(0))
         x_pin = x_full[:, c0:c1].contiguous().pin_memory()
-    x_blk = x_pin.to(dev)
     flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
-    hops = [x_blk] + [torch.empty_like(x_blk) for _ in range(K)]
+    # narrow blocks live in slabs with a 64-byte row stride (FeatureSplitOperator.block_slab; --no-pad: the dense stride)
+    make = (lambda: torch.empty((n, c1 - c0), dtype=torch.float32, device=dev)) if args.no_pad else \
+        (lambda: fs.block_slab(n, c1 - c0, dev))
+    hops = [make() for _ in range(K + 1)]
+    hops[0].copy_(x_pin)
     state = {}
 
     def hops_only():
@@ -832,11 +836,11 @@ def run_feature_split(args):
         hops[0].copy_(x_pin)
         hops_only()
         for k in ((1, K) if big else range(1, K + 1)):        # big graphs: first and last hop (each check downloads a slab)
-            ref = oracle_rows_arrays(sub_ptr, sub_idx, sub_val, hops[k - 1].cpu().numpy(), c1 - c0)
+            ref = oracle_rows_arrays(sub_ptr, sub_idx, sub_val, hops[k - 1].contiguous().cpu().numpy(), c1 - c0)
             got = hops[k][sample_t].cpu().numpy()
             worst = max(worst, float(np.abs(got - ref).max() / max(np.abs(ref).max(), 1e-30)))
         blk = op.spmm(hops[0], mode="exact")
-        ref1 = oracle_rows_arrays(sub_ptr, sub_idx, sub_val, hops[0].cpu().numpy(), c1 - c0)
+        ref1 = oracle_rows_arrays(sub_ptr, sub_idx, sub_val, hops[0].contiguous().cpu().numpy(), c1 - c0)
         bit_equal = bool(np.array_equal(blk[sample_t].cpu().numpy(), ref1))      # EXACT block == the reference's chain
         checked = ("rank 0 column block: every hop vs oracle fma chain on 2000 sampled rows (FAST, 1e-5); EXACT-mode block "
                    "bit-equal to the oracle chain on those rows")

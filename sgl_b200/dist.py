@@ -616,11 +616,26 @@ class FeatureSplitOperator:
         cuts = [min(d, align * ((units * p) // world)) for p in range(world)] + [d]
         return np.asarray(cuts, dtype=np.int64)
 
+    @staticmethod
+    def block_slab(n: int, width: int, device, dtype=torch.float32) -> torch.Tensor:
+        """[n, width] view of a slab whose row stride is rounded up to 16 floats for narrow blocks: every gathered row
+        then starts on a 64-byte boundary (a 48-byte row of a 12-column block touches two 32-byte sectors and one 128-byte
+        line instead of up to three sectors across two lines).  Blocks wider than 64 columns keep their own stride."""
+        ld = ((width + 15) // 16) * 16 if 0 < width <= 64 else width
+        return torch.empty((n, ld), dtype=dtype, device=device)[:, :width]
+
     def propagate(self, x_block: torch.Tensor, prop_steps: int) -> List[torch.Tensor]:
         """K hops of this rank's column block: [X[:, blk], (A^X)[:, blk], ...] -- no communication."""
-        hops = [x_block.contiguous()]
+        n, w = int(x_block.shape[0]), int(x_block.shape[1])
+        padded = x_block.is_cuda and w % 16 != 0 and w <= 64
+        if padded:
+            first = self.block_slab(n, w, x_block.device, x_block.dtype)
+            first.copy_(x_block)
+        else:
+            first = x_block.contiguous()
+        hops = [first]
         for _ in range(prop_steps):
-            out = torch.empty_like(hops[-1])
+            out = self.block_slab(n, w, x_block.device, x_block.dtype) if padded else torch.empty_like(hops[-1])
             self._hop(hops[-1], out)
             hops.append(out)
         return hops
