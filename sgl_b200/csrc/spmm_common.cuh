@@ -5,6 +5,12 @@
 
 #include "common.cuh"
 
+// L1 qualifier of the hinted gathers (experiment paths only): "" = default allocation, ".L1::no_allocate" to bypass.
+// Measured the same either way on products-shape (profiles/r02_cold_tags.txt).
+#ifndef SGL_HINT_L1
+#define SGL_HINT_L1 ""
+#endif
+
 namespace sglb200 {
 
 constexpr int kWarpsPerBlock = 8;
@@ -153,7 +159,7 @@ template <> struct Slice<4> {
     __device__ __forceinline__ void load_l2(const char *p) { v = __ldcg(reinterpret_cast<const ulonglong2 *>(p)); }
     __device__ __forceinline__ void load_hint(const char *p, uint64_t pol)
     {
-        asm volatile("ld.global.nc.L1::no_allocate.L2::cache_hint.v2.u64 {%0, %1}, [%2], %3;"
+        asm volatile("ld.global.nc" SGL_HINT_L1 ".L2::cache_hint.v2.u64 {%0, %1}, [%2], %3;"
                      : "=l"(v.x), "=l"(v.y) : "l"(p), "l"(pol));
     }
     __device__ __forceinline__ void add(const Slice &x)
@@ -188,7 +194,7 @@ template <> struct Slice<2> {
     __device__ __forceinline__ void load_l2(const char *p) { v = __ldcg(reinterpret_cast<const unsigned long long *>(p)); }
     __device__ __forceinline__ void load_hint(const char *p, uint64_t pol)
     {
-        asm volatile("ld.global.nc.L1::no_allocate.L2::cache_hint.u64 %0, [%1], %2;" : "=l"(v) : "l"(p), "l"(pol));
+        asm volatile("ld.global.nc" SGL_HINT_L1 ".L2::cache_hint.u64 %0, [%1], %2;" : "=l"(v) : "l"(p), "l"(pol));
     }
     __device__ __forceinline__ void add(const Slice &x) { asm("add.rn.f32x2 %0, %0, %1;" : "+l"(v) : "l"(x.v)); }
     __device__ __forceinline__ void store(char *p) const { *reinterpret_cast<unsigned long long *>(p) = v; }
@@ -211,7 +217,7 @@ template <> struct Slice<1> {
     __device__ __forceinline__ void load_l2(const char *p) { v = __ldcg(reinterpret_cast<const float *>(p)); }
     __device__ __forceinline__ void load_hint(const char *p, uint64_t pol)
     {
-        asm volatile("ld.global.nc.L1::no_allocate.L2::cache_hint.f32 %0, [%1], %2;" : "=f"(v) : "l"(p), "l"(pol));
+        asm volatile("ld.global.nc" SGL_HINT_L1 ".L2::cache_hint.f32 %0, [%1], %2;" : "=f"(v) : "l"(p), "l"(pol));
     }
     __device__ __forceinline__ void add(const Slice &x) { v = __fadd_rn(v, x.v); }
     __device__ __forceinline__ void store(char *p) const { *reinterpret_cast<float *>(p) = v; }
