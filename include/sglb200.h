@@ -104,6 +104,22 @@ SGLB200_API int sglb200_graph_info(sglb200_graph_t g, int64_t info[9]);
 SGLB200_API int sglb200_normalize_values(sglb200_graph_t g, const double *raw_w, const double *d_left, const double *d_right,
                              double alpha, int apply_ppr, int loc, void *stream);
 
+/* ---- f2: structure of A^ from a COO edge list, on the device (utils.py:76-78,87, laplacian_graph_op.py:19) -----
+ * rows / cols: n_edges int64 device arrays (duplicates allowed, any order), weights: n_edges float32 device or NULL (= 1).
+ * Builds A~ = A (+ I when add_identity) exactly as scipy does -- duplicates of A summed in float32 in input order, the
+ * identity added in float64, exact zeros dropped -- its float64 row sums `deg` (column order), and the CSR of the
+ * TRANSPOSE A~^T (= the structure of A^) with sorted columns.  Returns the number of stored entries in *nnz_out and an
+ * opaque builder; sglb200_adjacency_export writes indptr [n+1], indices [nnz] (int32), raw_w [nnz] (float64: the merged
+ * weight of A~[j,i] at position (i,j); may be NULL) and deg [n] (may be NULL) into caller-owned device buffers.
+ * n < 2^31, n_edges + n < 2^32.  Own radix sort / scan kernels, no host pass over the edges. */
+typedef struct sglb200_adj_builder sglb200_adj_builder;
+SGLB200_API int sglb200_adjacency_build(sglb200_adj_builder **out, int64_t n, int64_t n_edges, const int64_t *rows,
+                                        const int64_t *cols, const float *weights, int add_identity, int64_t *nnz_out,
+                                        void *stream);
+SGLB200_API int sglb200_adjacency_export(sglb200_adj_builder *b, int64_t *indptr, int32_t *indices, double *raw_w, double *deg,
+                                         void *stream);
+SGLB200_API void sglb200_adjacency_free(sglb200_adj_builder *b);
+
 /* ---- a5/a6/a7: one hop  Y = A X  (+ Y_in when accumulate != 0) ----------------------------------------------
  * X: [n_cols, d] float32 with row stride ldx (elements), Y: [n_rows, d] with row stride ldy; device pointers.
  * accumulate != 0 reproduces the reference kernel's `answer += ...` semantics (matmul.c:36-37): each chain

@@ -30,6 +30,10 @@ SIGNATURES = {
     "sglb200_graph_set_values": (c_int, [c_void_p, c_void_p, c_int, c_void_p]),
     "sglb200_graph_info": (c_int, [c_void_p, POINTER(c_int64)]),
     "sglb200_normalize_values": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_double, c_int, c_int, c_void_p]),
+    "sglb200_adjacency_build": (c_int, [POINTER(c_void_p), c_int64, c_int64, c_void_p, c_void_p, c_void_p, c_int,
+                                        POINTER(c_int64), c_void_p]),
+    "sglb200_adjacency_export": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p]),
+    "sglb200_adjacency_free": (None, [c_void_p]),
     "sglb200_spmm": (c_int, [c_void_p, c_void_p, c_int64, c_void_p, c_int64, c_int, c_int, c_int, c_void_p]),
     "sglb200_graph_chunks": (c_int, [c_void_p, c_int, c_int, POINTER(c_int64), POINTER(c_int64)]),
     "sglb200_spmm_tiles": (c_int, [c_void_p, c_void_p, c_int64, c_void_p, c_int64, c_int, c_int, c_int64, c_int64,

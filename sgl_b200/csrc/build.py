@@ -12,7 +12,7 @@ import sys
 HERE = os.path.dirname(os.path.abspath(__file__))
 PKG = os.path.dirname(HERE)
 ROOT = os.path.dirname(PKG)
-SOURCES = ["graph.cu", "spmm.cu", "spmm_group.cu", "spmm_tma.cu", "propagate.cu", "aggregate.cu", "learnable.cu", "iterate.cu", "legacy.cu", "peer.cu"]
+SOURCES = ["graph.cu", "build_adj.cu", "spmm.cu", "spmm_group.cu", "spmm_tma.cu", "propagate.cu", "aggregate.cu", "learnable.cu", "iterate.cu", "legacy.cu", "peer.cu"]
 HEADERS = ["common.cuh", "spmm_common.cuh", os.path.join(ROOT, "include", "sglb200.h")]
 OUT = os.path.join(PKG, "libsglb200.so")
 OBJ = os.path.join(HERE, "build")

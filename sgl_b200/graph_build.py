@@ -6,12 +6,15 @@ Restates what the reference does with scipy on one CPU core
     dL = deg^(r-1), dR = deg^(-r)       utils.py:79-85                 (inf -> 0)
     A^ = (A~ diag(dL))^T diag(dR)       utils.py:87, .tocsr() at graph_op/laplacian_graph_op.py:19
     (1-alpha) A^ + alpha I              graph_op/ppr_graph_op.py:19
-as sort / segment-reduce passes over the COO entries with torch on the GPU (memory + plumbing), and the value pass
-in libsglb200 (sglb200_normalize_values: IEEE float64 products in the reference's order).  The CSR structure
-(indptr, sorted indices) is bit-identical to the reference's; the float32 values are bit-identical when the degree
-powers are evaluated on the host (`pow_on="host"`: numpy/glibc pow, O(N)) and the weights are integers (every
-dataset of the reference: 1 or 2); `pow_on="device"` may differ by one float64 ulp before the
-float32 rounding (CUDA pow is <= 2 ulp).
+with our own device kernels: sglb200_adjacency_build (csrc/build_adj.cu: LSD radix sort of (row | col | identity) keys,
+run fold, per-row degree chains, transposing sort by column) for the structure, degrees and merged weights, and
+sglb200_normalize_values for the value pass (IEEE float64 products in the reference's order).  `engine="torch"` keeps the
+first version (torch.sort / segment_reduce) as an independent cross-check for the tests.  The CSR structure (indptr,
+sorted indices) and the degrees are bit-identical to the reference's; the float32 values are bit-identical when the
+degree powers come from numpy's pow (`pow_on="host"`, the default: evaluated on a table of the distinct integer degrees
+-- max_deg + 1 entries -- when every degree is an integer, which holds for every dataset of the reference (weights 1 or 2,
+SURVEY.md section 9.3); only non-integer degree vectors make the O(N) round trip); `pow_on="device"` may differ by one
+float64 ulp before the float32 rounding (CUDA pow is <= 2 ulp).
 """
 from __future__ import annotations
 
@@ -20,7 +23,11 @@ from typing import Optional
 import numpy as np
 import torch
 
-from .runtime import CsrOperator, require_cuda
+from ctypes import byref, c_int64, c_void_p
+
+from . import _lib
+from ._lib import check
+from .runtime import CsrOperator, _stream_ptr, require_cuda
 
 
 def _segment_sum_sorted(values: torch.Tensor, first: torch.Tensor) -> torch.Tensor:
@@ -41,11 +48,72 @@ def merge_duplicates(keys: torch.Tensor, w: torch.Tensor):
     return keys[first], _segment_sum_sorted(w, first)
 
 
+def adjacency_structure_native(rows: torch.Tensor, cols: torch.Tensor, n: int, weights: Optional[torch.Tensor] = None):
+    """(indptr int64 [n+1], indices int32 [nnz], raw_w float64 [nnz], deg float64 [n]) of (A + I)^T through
+    sglb200_adjacency_build / _export -- hand-written sort, fold and degree kernels, nothing leaves the device."""
+    require_cuda()
+    dev = rows.device
+    rows = rows.to(torch.int64).contiguous()
+    cols = cols.to(torch.int64).contiguous()
+    w = None if weights is None else weights.to(device=dev, dtype=torch.float32).contiguous()
+    lib = _lib.load()
+    h, nnz = c_void_p(), c_int64(0)
+    with torch.cuda.device(dev):
+        check(lib.sglb200_adjacency_build(byref(h), int(n), int(rows.numel()), c_void_p(rows.data_ptr()),
+                                          c_void_p(cols.data_ptr()), None if w is None else c_void_p(w.data_ptr()), 1,
+                                          byref(nnz), _stream_ptr()), "adjacency_build")
+        try:
+            indptr = torch.empty(n + 1, dtype=torch.int64, device=dev)
+            indices = torch.empty(nnz.value, dtype=torch.int32, device=dev)
+            raw_w = torch.empty(nnz.value, dtype=torch.float64, device=dev)
+            deg = torch.empty(n, dtype=torch.float64, device=dev)
+            check(lib.sglb200_adjacency_export(h, c_void_p(indptr.data_ptr()), c_void_p(indices.data_ptr()),
+                                               c_void_p(raw_w.data_ptr()), c_void_p(deg.data_ptr()), _stream_ptr()),
+                  "adjacency_export")
+            torch.cuda.current_stream().synchronize()
+        finally:
+            lib.sglb200_adjacency_free(h)
+    return indptr, indices, raw_w, deg
+
+
+_POW_TABLE_MAX = 1 << 22
+
+
+def degree_powers(deg: torch.Tensor, r: float, pow_on: str = "host"):
+    """(deg^(r-1), deg^(-r)) as float64 device vectors, inf -> 0 (utils.py:79-85).  pow_on="host": numpy's pow, like the
+    reference -- on the table 0..max_deg when the degrees are integers (the vector itself never leaves the device)."""
+    dev = deg.device
+    if pow_on != "host":
+        d_left, d_right = torch.pow(deg, r - 1), torch.pow(deg, -r)
+        d_left[torch.isinf(d_left)] = 0.0
+        d_right[torch.isinf(d_right)] = 0.0
+        return d_left, d_right
+    top = float(deg.max()) if deg.numel() else 0.0
+    integral = deg.numel() > 0 and 0 <= top < _POW_TABLE_MAX and bool((deg == torch.floor(deg)).all()) and float(deg.min()) >= 0
+    src = np.arange(int(top) + 1, dtype=np.float64) if integral else deg.cpu().numpy()
+    with np.errstate(divide="ignore", invalid="ignore"):
+        dl, dr = np.power(src, r - 1), np.power(src, -r)
+    dl[np.isinf(dl)] = 0.0
+    dr[np.isinf(dr)] = 0.0
+    d_left, d_right = torch.from_numpy(dl).to(dev), torch.from_numpy(dr).to(dev)
+    if integral:
+        idx = deg.to(torch.int64)
+        d_left, d_right = d_left[idx], d_right[idx]
+    return d_left, d_right
+
+
 def normalized_adjacency_device(rows: torch.Tensor, cols: torch.Tensor, n: int, weights: Optional[torch.Tensor] = None,
-                                r: float = 0.5, alpha: Optional[float] = None, pow_on: str = "host"):
+                                r: float = 0.5, alpha: Optional[float] = None, pow_on: str = "host", engine: str = "native"):
     """COO of A on the device (int64 ids, duplicates allowed, float32 weights or None = 1) ->
     dict(indptr int64 [n+1], indices int32 [nnz], raw_w float64 [nnz], d_left, d_right float64 [n], deg) on the
     device, describing A^ = diag(dL) (A+I)^T diag(dR) before the value pass."""
+    if engine == "native":
+        indptr, indices, raw_w, deg = adjacency_structure_native(rows, cols, n, weights)
+        d_left, d_right = degree_powers(deg, r, pow_on)
+        return {"indptr": indptr, "indices": indices, "raw_w": raw_w, "d_left": d_left, "d_right": d_right, "deg": deg,
+                "alpha": alpha}
+    if engine != "torch":
+        raise ValueError("engine must be 'native' or 'torch'")
     dev = rows.device
     rows = rows.to(torch.int64)
     cols = cols.to(torch.int64)
@@ -64,17 +132,7 @@ def normalized_adjacency_device(rows: torch.Tensor, cols: torch.Tensor, n: int, 
     first[1:] = r_t[1:] != r_t[:-1]
     deg = torch.zeros(n, dtype=torch.float64, device=dev)
     deg[r_t[first]] = _segment_sum_sorted(w2, first)                     # weighted degrees, column order
-    if pow_on == "host":
-        d = deg.cpu().numpy()
-        with np.errstate(divide="ignore", invalid="ignore"):
-            dl, dr = np.power(d, r - 1), np.power(d, -r)
-        dl[np.isinf(dl)] = 0.0
-        dr[np.isinf(dr)] = 0.0
-        d_left, d_right = torch.from_numpy(dl).to(dev), torch.from_numpy(dr).to(dev)
-    else:
-        d_left, d_right = torch.pow(deg, r - 1), torch.pow(deg, -r)
-        d_left[torch.isinf(d_left)] = 0.0
-        d_right[torch.isinf(d_right)] = 0.0
+    d_left, d_right = degree_powers(deg, r, pow_on)
     # transpose: entry (j, i) of A~ lives at (i, j) of A^
     keys_t, order = torch.sort(c_t * n + r_t, stable=True)
     out_rows = torch.div(keys_t, n, rounding_mode="floor")
@@ -109,10 +167,10 @@ def parts_to_scipy(parts):
                          shape=(n, n))
 
 
-def build_operator_device(rows, cols, n, weights=None, r=0.5, alpha=None, pow_on="host", **op_kw) -> CsrOperator:
+def build_operator_device(rows, cols, n, weights=None, r=0.5, alpha=None, pow_on="host", engine="native", **op_kw) -> CsrOperator:
     """CsrOperator of A^ (LaplacianGraphOp semantics, or PprGraphOp when alpha is given) without any host scipy."""
     require_cuda()
-    parts = normalized_adjacency_device(rows, cols, n, weights, r, alpha, pow_on)
+    parts = normalized_adjacency_device(rows, cols, n, weights, r, alpha, pow_on, engine)
     op = CsrOperator(parts["indptr"], parts["indices"], None, (n, n), **op_kw)
     op.normalize_values(parts["raw_w"], parts["d_left"], parts["d_right"], alpha=alpha or 0.0,
                         apply_ppr=alpha is not None)

@@ -18,7 +18,7 @@ import torch
 import torch.nn.functional as F
 
 from . import _lib
-from .graph_build import normalized_adjacency_device
+from .graph_build import degree_powers, normalized_adjacency_device
 from .runtime import CsrOperator, aggregate, require_cuda
 
 
@@ -74,15 +74,12 @@ def nafs_smoothed_features(adj, features, hops: int, r_list: Sequence[float] = (
                                         torch.from_numpy(coo.col.astype(np.int64)).to(dev), adj.shape[0],
                                         torch.from_numpy(np.asarray(coo.data, dtype=np.float32)).to(dev), r=float(r_list[0]))
     op = CsrOperator(parts["indptr"], parts["indices"], None, adj.shape)
-    deg = parts["deg"].cpu().numpy()
+    deg = parts["deg"]
     per_r = []
     try:
         for r in r_list:
-            with np.errstate(divide="ignore", invalid="ignore"):
-                dl, dr = np.power(deg, r - 1), np.power(deg, -r)
-            dl[np.isinf(dl)] = 0.0
-            dr[np.isinf(dr)] = 0.0
-            op.normalize_values(parts["raw_w"], torch.from_numpy(dl).to(dev), torch.from_numpy(dr).to(dev))
+            dl, dr = degree_powers(deg, float(r))        # numpy pow on the table of distinct integer degrees
+            op.normalize_values(parts["raw_w"], dl, dr)
             hop_list = op.propagate(x, hops, mode=mode)
             if method == "simple":
                 per_r.append(hop_list[-1])
@@ -121,15 +118,12 @@ def nafs_smoothed_features_sweep(adj, features, max_hops: int, r_list: Sequence[
                                         torch.from_numpy(coo.col.astype(np.int64)).to(dev), adj.shape[0],
                                         torch.from_numpy(np.asarray(coo.data, dtype=np.float32)).to(dev), r=float(r_list[0]))
     op = CsrOperator(parts["indptr"], parts["indices"], None, adj.shape)
-    deg = parts["deg"].cpu().numpy()
+    deg = parts["deg"]
     per_hop = [[] for _ in range(max_hops)]          # per_hop[h-1] = one tensor per r
     try:
         for r in (r_list[:1] if method == "simple" else r_list):
-            with np.errstate(divide="ignore", invalid="ignore"):
-                dl, dr = np.power(deg, r - 1), np.power(deg, -r)
-            dl[np.isinf(dl)] = 0.0
-            dr[np.isinf(dr)] = 0.0
-            op.normalize_values(parts["raw_w"], torch.from_numpy(dl).to(dev), torch.from_numpy(dr).to(dev))
+            dl, dr = degree_powers(deg, float(r))        # numpy pow on the table of distinct integer degrees
+            op.normalize_values(parts["raw_w"], dl, dr)
             hop_list = op.propagate(x, max_hops, mode=mode)
             for h in range(1, max_hops + 1):
                 per_hop[h - 1].append(hop_list[h] if method == "simple" else aggregate(_lib.AGG_OSD, hop_list[:h + 1]))

@@ -464,6 +464,98 @@ def test_device_builder_larger_random_vs_oracle():
         op.close()
 
 
+def _scipy_structure(rows, cols, w, n):
+    """What the reference computes on the host (utils.py:76-78,87): A canonical, A + I, row sums, transpose in CSR order."""
+    import scipy.sparse as sp
+    a = sp.csr_matrix((w, (rows, cols)), shape=(n, n))
+    a.sum_duplicates()
+    at = a + sp.eye(n)
+    deg = np.asarray(at.sum(1)).reshape(-1)
+    t = sp.csr_matrix(at.T)
+    t.sort_indices()
+    return t.indptr.astype(np.int64), t.indices.astype(np.int32), t.data.astype(np.float64), deg
+
+
+@pytest.mark.parametrize("n,e,seed", [(1, 0, 0), (7, 0, 1), (300, 4000, 2), (5000, 70000, 3), (70001, 900000, 4)])
+def test_native_adjacency_builder_vs_scipy(n, e, seed):
+    """sglb200_adjacency_build (own radix sort / scan / fold kernels): unsorted COO with duplicates, self loops, a
+    diagonal entry of -1 (A + I makes an exact zero, which scipy drops), asymmetric, integer weights 1..3 so that every
+    float32 duplicate sum is exact whatever the order.  Structure, merged weights and degrees equal scipy's bit for bit;
+    the torch engine (first version) agrees too."""
+    from sgl_b200.graph_build import adjacency_structure_native, normalized_adjacency_device
+    rng = np.random.default_rng(seed)
+    rows = rng.integers(0, n, e).astype(np.int64)
+    cols = ((rng.zipf(1.3, e) - 1) % n).astype(np.int64)
+    w = rng.integers(1, 4, e).astype(np.float32)
+    if e:
+        k = e // 10
+        rows[:k], cols[:k] = rows[e - k:], cols[e - k:]          # duplicates far apart in the input
+        rows[k:2 * k] = cols[k:2 * k]                            # self loops
+        sel = rows == cols                                       # one diagonal entry summing to -1: dropped by A + I
+        if sel.any():
+            v = int(rows[sel][0])
+            hit = (rows == v) & (cols == v)
+            w[hit] = 0.0
+            w[np.flatnonzero(hit)[0]] = -1.0
+    for weights in ((w, None) if e else (None,)):
+        ww = np.ones(e, dtype=np.float32) if weights is None else weights
+        ref_ptr, ref_idx, ref_w, ref_deg = _scipy_structure(rows, cols, ww, n)
+        rt, ct = torch.from_numpy(rows).cuda(), torch.from_numpy(cols).cuda()
+        wt = None if weights is None else torch.from_numpy(weights).cuda()
+        indptr, indices, raw_w, deg = adjacency_structure_native(rt, ct, n, wt)
+        assert np.array_equal(indptr.cpu().numpy(), ref_ptr)
+        assert np.array_equal(indices.cpu().numpy(), ref_idx)
+        assert np.array_equal(raw_w.cpu().numpy(), ref_w)
+        assert np.array_equal(deg.cpu().numpy(), ref_deg)
+        if e:
+            parts_t = normalized_adjacency_device(rt, ct, n, wt, engine="torch")
+            parts_n = normalized_adjacency_device(rt, ct, n, wt, engine="native")
+            for key in ("indptr", "indices", "raw_w", "deg", "d_left", "d_right"):
+                assert torch.equal(parts_t[key], parts_n[key]), key
+
+
+def test_native_adjacency_builder_float_weights_input_order():
+    """Non-integer weights: duplicates are added in float32 in INPUT order (the stable sort keeps it), then widened."""
+    from sgl_b200.graph_build import adjacency_structure_native
+    rng = np.random.default_rng(9)
+    n, e = 50, 3000
+    rows, cols = rng.integers(0, n, e).astype(np.int64), rng.integers(0, n, e).astype(np.int64)
+    w = rng.standard_normal(e).astype(np.float32)
+    acc = {}
+    for r, c, v in zip(rows.tolist(), cols.tolist(), w):
+        acc[(r, c)] = np.float32(acc[(r, c)] + v) if (r, c) in acc else np.float32(v)
+    dense = np.zeros((n, n), dtype=np.float64)
+    for (r, c), v in acc.items():
+        dense[r, c] = float(v)
+    dense += np.eye(n)
+    indptr, indices, raw_w, deg = adjacency_structure_native(torch.from_numpy(rows).cuda(), torch.from_numpy(cols).cuda(), n,
+                                                             torch.from_numpy(w).cuda())
+    indptr, indices, raw_w = indptr.cpu().numpy(), indices.cpu().numpy(), raw_w.cpu().numpy()
+    got = np.zeros((n, n), dtype=np.float64)
+    for i in range(n):
+        js = indices[indptr[i]:indptr[i + 1]]
+        assert np.all(np.diff(js) > 0)
+        got[js, i] = raw_w[indptr[i]:indptr[i + 1]]                 # entry (i, j) of the transpose holds A~[j, i]
+    assert np.array_equal(got, dense)
+    want_deg = np.zeros(n, dtype=np.float64)
+    for i in range(n):
+        acc_i = 0.0                                                 # one sequential float64 chain in column order
+        for j in range(n):
+            if dense[i, j] != 0.0:
+                acc_i = acc_i + float(dense[i, j])
+        want_deg[i] = acc_i
+    assert np.array_equal(deg.cpu().numpy(), want_deg)
+
+
+def test_native_adjacency_builder_rejects_bad_edges():
+    from sgl_b200 import SglB200Error
+    from sgl_b200.graph_build import adjacency_structure_native
+    rows = torch.tensor([0, 5], dtype=torch.int64, device="cuda")
+    cols = torch.tensor([1, 2], dtype=torch.int64, device="cuda")
+    with pytest.raises(SglB200Error, match="outside"):
+        adjacency_structure_native(rows, cols, 4, None)
+
+
 def test_row_partition_single_rank_on_cuda():
     """world = 1 degenerates to the single-GPU operator; exercises DistOperator's CUDA path without NCCL."""
     from sgl_b200.dist import DistOperator, build_plan
