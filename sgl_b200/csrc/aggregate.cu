@@ -11,6 +11,7 @@
 #include <math.h>
 
 #include "common.cuh"
+#include "trace.cuh"
 
 namespace sglb200 {
 
@@ -263,6 +264,7 @@ int sglb200_aggregate(int op, const float *const *feats, int n_feats, int64_t n,
                       const float *weights, float *out, int64_t ld_out, void *stream_)
 {
     clear_error();
+    TraceRange range("sglb200_aggregate");
     SGL_REQUIRE(feats && out, "aggregate: NULL argument");
     SGL_REQUIRE(n_feats >= 1 && n_feats <= kMaxFeats, "aggregate: n_feats=%d outside [1,%d]", n_feats, kMaxFeats);
     SGL_REQUIRE(n >= 0 && d >= 0 && ld_in >= d, "aggregate: bad sizes");

@@ -13,7 +13,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 PKG = os.path.dirname(HERE)
 ROOT = os.path.dirname(PKG)
 SOURCES = ["graph.cu", "build_adj.cu", "spmm.cu", "spmm_group.cu", "spmm_tma.cu", "propagate.cu", "aggregate.cu", "learnable.cu", "iterate.cu", "legacy.cu", "peer.cu"]
-HEADERS = ["common.cuh", "spmm_common.cuh", os.path.join(ROOT, "include", "sglb200.h")]
+HEADERS = ["common.cuh", "spmm_common.cuh", "trace.cuh", os.path.join(ROOT, "include", "sglb200.h")]
 OUT = os.path.join(PKG, "libsglb200.so")
 OBJ = os.path.join(HERE, "build")
 NVCC = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
@@ -51,7 +51,7 @@ def build(force=False, verbose=False):
         objs.append(op)
     if rebuilt or not os.path.exists(OUT):
         # host compiler: the distro g++ (the image's CC/CXX wrappers lack some specs)
-        cmd = [NVCC, "-shared", "-o", OUT] + objs + ["-gencode", "arch=compute_100a,code=sm_100a", "-cudart", "static"]
+        cmd = [NVCC, "-shared", "-o", OUT] + objs + ["-gencode", "arch=compute_100a,code=sm_100a", "-cudart", "static", "-ldl"]
         if verbose:
             print(" ".join(cmd))
         subprocess.check_call(cmd)

@@ -18,6 +18,7 @@
 #include <new>
 
 #include "common.cuh"
+#include "trace.cuh"
 
 struct sglb200_adj_builder {
     int64_t n = 0;
@@ -379,6 +380,7 @@ extern "C" int sglb200_adjacency_build(sglb200_adj_builder **out, int64_t n, int
                                        const float *weights, int add_identity, int64_t *nnz_out, void *stream_)
 {
     clear_error();
+    TraceRange range("sglb200_adjacency_build");
     SGL_REQUIRE(out != nullptr && nnz_out != nullptr, "adjacency_build: out / nnz_out is NULL");
     SGL_REQUIRE(n > 0 && n < (1LL << 31), "adjacency_build: n = %lld must be in [1, 2^31)", (long long)n);
     SGL_REQUIRE(n_edges >= 0 && (n_edges == 0 || (rows && cols)), "adjacency_build: bad edge list");

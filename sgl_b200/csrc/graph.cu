@@ -13,6 +13,7 @@
 #include <vector>
 
 #include "common.cuh"
+#include "trace.cuh"
 
 namespace sglb200 {
 
@@ -461,6 +462,7 @@ int sglb200_graph_create(sglb200_graph_t *out, int64_t n_rows, int64_t n_cols, i
                          int split_threshold, void *stream_)
 {
     clear_error();
+    TraceRange range("sglb200_graph_create");
     SGL_REQUIRE(out != nullptr, "graph_create: out is NULL");
     *out = nullptr;
     SGL_REQUIRE(n_rows >= 0 && n_cols >= 0 && nnz >= 0, "graph_create: negative size");
@@ -660,6 +662,7 @@ int sglb200_normalize_values(sglb200_graph_t g, const double *raw_w, const doubl
                              double alpha, int apply_ppr, int loc, void *stream_)
 {
     clear_error();
+    TraceRange range("sglb200_normalize_values");
     SGL_REQUIRE(g && raw_w && d_left && d_right, "normalize_values: NULL argument");
     SGL_REQUIRE(g->n_rows == g->n_cols, "normalize_values: operator must be square");
     g->pairs_valid = false;

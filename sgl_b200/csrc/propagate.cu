@@ -20,6 +20,7 @@
 #include <stdlib.h>
 
 #include "spmm_common.cuh"
+#include "trace.cuh"
 
 namespace sglb200 {
 
@@ -147,6 +148,7 @@ int sglb200_propagate_fused(sglb200_graph_t g, const float *X, int64_t ldx, floa
                             int64_t ld_out, int fuse_norm, void *stream_)
 {
     clear_error();
+    TraceRange range("sglb200_propagate_fused");
     SGL_REQUIRE(g && X, "propagate_fused: NULL argument");
     SGL_REQUIRE(K >= 0 && d >= 0, "propagate_fused: negative size");
     SGL_REQUIRE(g->n_rows == g->n_cols, "propagate_fused: operator must be square");
@@ -230,6 +232,8 @@ int sglb200_propagate_fused(sglb200_graph_t g, const float *X, int64_t ldx, floa
         ld_in = d;
     }
     // ---- hops 1..K ------------------------------------------------------------------------------------------------------
+    HopTimer timer("propagate_fused");
+    timer.mark(stream);
     for (int k = 1; k <= K; ++k) {
         Epilogue e = {};
         bool need_epi = false;
@@ -294,9 +298,11 @@ int sglb200_propagate_fused(sglb200_graph_t g, const float *X, int64_t ldx, floa
         }
         const int st = spmm_launch_ex(g, in, ld_in, Y, ldy, d, mode, 0, 0, -1, need_epi ? &e : nullptr, fused ? 1 : 0, stream);
         if (st != SGLB200_OK) return st;
+        timer.mark(stream);
         in = next_in;
         ld_in = ld_next;
     }
+    timer.report();
     if (mean_div != 0.0f && last >= 1) {
         const int64_t total = n * d;
         int64_t blocks = (total + 255) / 256;

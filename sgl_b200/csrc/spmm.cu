@@ -26,6 +26,7 @@
 #include <algorithm>
 
 #include "spmm_common.cuh"
+#include "trace.cuh"
 
 namespace sglb200 {
 
@@ -1026,6 +1027,7 @@ int sglb200_spmm(sglb200_graph_t g, const float *X, int64_t ldx, float *Y, int64
                  int accumulate, void *stream)
 {
     clear_error();
+    TraceRange range("sglb200_spmm");
     return spmm_launch(g, X, ldx, Y, ldy, d, mode, accumulate, (cudaStream_t)stream);
 }
 
@@ -1042,11 +1044,16 @@ int sglb200_propagate(sglb200_graph_t g, float *const *hops, int64_t ld, int d, 
     SGL_REQUIRE(g && hops, "propagate: NULL argument");
     SGL_REQUIRE(K >= 0, "propagate: negative prop_steps");
     SGL_REQUIRE(g->n_rows == g->n_cols, "propagate: operator must be square (use sglb200_spmm for row partitions)");
+    TraceRange range("sglb200_propagate");
+    HopTimer timer("propagate");
+    timer.mark((cudaStream_t)stream);
     for (int k = 1; k <= K; ++k) {
         SGL_REQUIRE(hops[k] != hops[k - 1], "propagate: hop %d aliases hop %d", k, k - 1);
         const int st = spmm_launch(g, hops[k - 1], ld, hops[k], ld, d, mode, 0, (cudaStream_t)stream);
         if (st != SGLB200_OK) return st;
+        timer.mark((cudaStream_t)stream);
     }
+    timer.report();
     return SGLB200_OK;
 }
 
@@ -1067,14 +1074,18 @@ int sglb200_propagate_host(sglb200_graph_t g, const float *X, float *const *hops
     // host on the copy stream; slab k%3 is reused only after the download of hop k-3 has finished.
     cudaStream_t cs = g->copy_stream;  // uploads + downloads
     cudaStream_t ks = nullptr;         // kernels on the legacy default stream of the caller's thread
+    TraceRange range("sglb200_propagate_host");
+    HopTimer timer("propagate_host");
     SGL_CUDA_CHECK(cudaMemcpyAsync(g->stage[0], X, slab * sizeof(float), cudaMemcpyHostToDevice, cs));
     SGL_CUDA_CHECK(cudaEventRecord(g->ev_copy[0], cs));
     SGL_CUDA_CHECK(cudaStreamWaitEvent(ks, g->ev_copy[0], 0));
+    timer.mark(ks);
     for (int k = 1; k <= K; ++k) {
         const int dst = k % 3, src = (k - 1) % 3;
         if (k >= 3) SGL_CUDA_CHECK(cudaStreamWaitEvent(ks, g->ev_copy[dst], 0));  // download of hop k-3 done
         const int st = spmm_launch(g, g->stage[src], d, g->stage[dst], d, d, mode, 0, ks);
         if (st != SGLB200_OK) return st;
+        timer.mark(ks);
         SGL_CUDA_CHECK(cudaEventRecord(g->ev_compute[dst], ks));
         if (hops_out[k - 1]) {
             SGL_CUDA_CHECK(cudaStreamWaitEvent(cs, g->ev_compute[dst], 0));
@@ -1084,6 +1095,7 @@ int sglb200_propagate_host(sglb200_graph_t g, const float *X, float *const *hops
     }
     SGL_CUDA_CHECK(cudaStreamSynchronize(ks));
     SGL_CUDA_CHECK(cudaStreamSynchronize(cs));
+    timer.report();
     return SGLB200_OK;
 }
 

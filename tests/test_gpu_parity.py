@@ -13,7 +13,7 @@ import pytest
 import scipy.sparse as sp
 import torch
 
-from conftest import GRAPH_TAGS, golden_graph_files, load_graph
+from conftest import GRAPH_TAGS, ROOT, golden_graph_files, load_graph
 from oracle import sgap_oracle as O
 
 pytestmark = pytest.mark.gpu
@@ -554,6 +554,24 @@ def test_native_adjacency_builder_rejects_bad_edges():
     cols = torch.tensor([1, 2], dtype=torch.int64, device="cuda")
     with pytest.raises(SglB200Error, match="outside"):
         adjacency_structure_native(rows, cols, 4, None)
+
+
+def test_trace_mode_prints_per_hop_timers():
+    """SGLB200_TRACE=1: CUDA-event timers around every hop of sglb200_propagate, one stderr line per hop (the NVTX ranges
+    around the entry points need a profiler to be seen; this is the part a test can check)."""
+    import subprocess
+    import sys
+    code = ("import numpy as np, scipy.sparse as sp, torch\n"
+            "from sgl_b200.runtime import CsrOperator\n"
+            "a = sp.random(500, 500, 0.02, format='csr', dtype=np.float32, random_state=1)\n"
+            "op = CsrOperator.from_scipy(a)\n"
+            "h = op.propagate(torch.ones(500, 8, device='cuda'), 3)\n"
+            "torch.cuda.synchronize(); print(float(h[-1].sum()))\n")
+    env = dict(os.environ, SGLB200_TRACE="1", PYTHONPATH=ROOT + os.pathsep + os.environ.get("PYTHONPATH", ""))
+    r = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True, env=env, timeout=300)
+    assert r.returncode == 0, r.stderr[-2000:]
+    lines = [ln for ln in r.stderr.splitlines() if ln.startswith("sglb200 trace: propagate hop")]
+    assert len(lines) == 3 and "sglb200 trace: propagate 3 hops" in r.stderr
 
 
 def test_row_partition_single_rank_on_cuda():
