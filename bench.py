@@ -64,6 +64,9 @@ def parse_args():
                     help="experiment: relabel the vertices by descending degree before building A^")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--split-one", action="store_true",
+                    help="run the feature-split harness on ONE rank (under torchrun --nproc-per-node 1): with --feat-dim d/N this is "
+                         "the per-rank work of an N-way split of a graph too large to run N-way within the GPU budget")
     ap.add_argument("--no-pad", action="store_true", help="feature split: dense row stride for narrow column blocks")
     ap.add_argument("--no-comparators", action="store_true")
     ap.add_argument("--traffic", default="ncu", choices=["ncu", "file", "none"],
@@ -405,7 +408,7 @@ def run_b200(args):
     import torch
     if args.traffic_child:
         return run_traffic_child(args)
-    if args.gpus > 1 or int(os.environ.get("WORLD_SIZE", "1")) > 1:
+    if args.gpus > 1 or int(os.environ.get("WORLD_SIZE", "1")) > 1 or args.split_one:
         return run_feature_split(args) if args.partition == "feature" else run_row_partition(args)
     from sgl_b200.graph_build import build_operator_device, parts_to_scipy
 
@@ -863,7 +866,10 @@ def run_feature_split(args):
                 "warmup": max(args.warmup, 3), "ms_per_step": 1e3 * total_s / args.steps, "higher_is_better": True,
                 "scaling": "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
                 "config": workload_config(name, n, nnz, d, K, args),
-                "partition": f"feature split x{world}: A^ replicated, column blocks {widths}, no per-hop exchange, one "
+                "partition": (f"ONE rank of a feature split measured alone (--split-one): the whole A^ with a column block of {widths[0]} "
+                              "features -- the per-rank work of an N-way split with d = N x this width; value counts this rank's "
+                              "non-zeros, an N-rank job delivers the same non-zeros per second at N x the width") if args.split_one else
+                             f"feature split x{world}: A^ replicated, column blocks {widths}, no per-hop exchange, one "
                              "all-to-all of hop K into row shards per step",
                 "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak * world, "unit": "GB/s",
                              "frac": achieved / (peak * world), "traffic": None,

@@ -270,12 +270,12 @@ __global__ void make_keys_kernel(const int64_t *__restrict__ rows, const int64_t
 
 // One thread per sorted item; the first item of a (row, col) run folds the run: float32 sum of A's entries in input order,
 // widened to float64, + 1.0 when the identity entry is there.  keep = run head with a non-zero result.
-__global__ void fold_runs_kernel(const uint64_t *__restrict__ keys, const float *__restrict__ vals, int64_t count, uint32_t *__restrict__ keep,
+__global__ void fold_runs_kernel(const uint64_t *__restrict__ keys, const float *__restrict__ vals, int64_t count, uint8_t *__restrict__ keep,
                                  double *__restrict__ folded)
 {
     for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < count; i += (int64_t)gridDim.x * blockDim.x) {
         const uint64_t id = keys[i] >> 1;
-        uint32_t k = 0;
+        uint8_t k = 0;
         if (i == 0 || (keys[i - 1] >> 1) != id) {
             float s = 0.0f;
             bool any = false, ident = false;
@@ -290,24 +290,39 @@ __global__ void fold_runs_kernel(const uint64_t *__restrict__ keys, const float 
             }
             const double w2 = (any ? (double)s : 0.0) + (ident ? 1.0 : 0.0);
             folded[i] = w2;
-            k = w2 != 0.0 ? 1u : 0u;
+            k = w2 != 0.0 ? 1 : 0;
         }
         keep[i] = k;
     }
 }
 
-__global__ void compact_kernel(const uint64_t *__restrict__ keys, const uint32_t *__restrict__ keep, const int64_t *__restrict__ pos,
-                               const double *__restrict__ folded, int64_t count, int col_bits, int32_t *__restrict__ row_of,
-                               uint32_t *__restrict__ col_of, uint32_t *__restrict__ ident_perm, double *__restrict__ w2)
+// Stream compaction without a global position array: every block re-scans its chunk of keep flags and starts at the
+// scanned count of the chunks before it.
+__global__ void __launch_bounds__(kScanThreads) compact_kernel(const uint64_t *__restrict__ keys, const uint8_t *__restrict__ keep,
+                                                               const int64_t *__restrict__ chunk_base, const double *__restrict__ folded, int64_t count,
+                                                               int col_bits, int32_t *__restrict__ row_of, uint32_t *__restrict__ col_of,
+                                                               uint32_t *__restrict__ ident_perm, double *__restrict__ w2)
 {
     const uint64_t col_mask = (1ULL << col_bits) - 1ULL;
-    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < count; i += (int64_t)gridDim.x * blockDim.x) {
-        if (!keep[i]) continue;
-        const int64_t p = pos[i];
-        row_of[p] = (int32_t)(keys[i] >> (col_bits + 1));
-        col_of[p] = (uint32_t)((keys[i] >> 1) & col_mask);
+    const int64_t base = (int64_t)blockIdx.x * kScanChunk + (int64_t)threadIdx.x * kScanItems;
+    uint8_t k[kScanItems];
+    int64_t mine = 0;
+#pragma unroll
+    for (int i = 0; i < kScanItems; ++i) {
+        k[i] = base + i < count ? keep[base + i] : 0;
+        mine += k[i];
+    }
+    int64_t total;
+    int64_t p = block_exclusive_scan<uint8_t>(mine, &total) + chunk_base[blockIdx.x];
+#pragma unroll
+    for (int i = 0; i < kScanItems; ++i) {
+        if (!k[i]) continue;
+        const uint64_t key = keys[base + i];
+        row_of[p] = (int32_t)(key >> (col_bits + 1));
+        col_of[p] = (uint32_t)((key >> 1) & col_mask);
         ident_perm[p] = (uint32_t)p;
-        w2[p] = folded[i];
+        w2[p] = folded[base + i];
+        ++p;
     }
 }
 
@@ -400,8 +415,9 @@ extern "C" int sglb200_adjacency_build(sglb200_adj_builder **out, int64_t n, int
     b->n = n;
     uint64_t *keys_a = nullptr, *keys_b = nullptr;
     float *vals_a = nullptr, *vals_b = nullptr;
-    uint32_t *keep = nullptr, *col_a = nullptr, *perm_a = nullptr;
-    int64_t *pos = nullptr, *row_ptr = nullptr, *scratch = nullptr;
+    uint8_t *keep = nullptr;
+    uint32_t *col_a = nullptr, *perm_a = nullptr;
+    int64_t *chunk_count = nullptr, *chunk_base = nullptr, *row_ptr = nullptr, *scratch = nullptr;
     int *bad = nullptr;
     SortWorkspace ws;
     int status = SGLB200_OK;
@@ -431,39 +447,54 @@ extern "C" int sglb200_adjacency_build(sglb200_adj_builder **out, int64_t n, int
     else ADJ_TRY((radix_sort<uint64_t, float, false>(keys_a, keys_b, nullptr, nullptr, total, 2 * col_bits + 1, &ws, &in_a, stream)));
     uint64_t *keys = in_a ? keys_a : keys_b, *spare = in_a ? keys_b : keys_a;   // the spare key buffer holds the folded weights
     const float *vals = has_vals ? (in_a ? vals_a : vals_b) : nullptr;
-    ADJ_TRY(cudaMalloc(&keep, sizeof(uint32_t) * total));
-    ADJ_TRY(cudaMalloc(&pos, sizeof(int64_t) * total));
-    ADJ_TRY(cudaMalloc(&scratch, sizeof(int64_t) * scan_scratch_elems(total)));
+    const int64_t chunks = (total + kScanChunk - 1) / kScanChunk;
+    ADJ_TRY(cudaMalloc(&keep, sizeof(uint8_t) * total));
+    ADJ_TRY(cudaMalloc(&chunk_count, sizeof(int64_t) * chunks));
+    ADJ_TRY(cudaMalloc(&chunk_base, sizeof(int64_t) * chunks));
+    ADJ_TRY(cudaMalloc(&scratch, sizeof(int64_t) * scan_scratch_elems(chunks)));
     if (e == cudaSuccess) {
         fold_runs_kernel<<<grid_for(total), 256, 0, stream>>>(keys, vals, total, keep, reinterpret_cast<double *>(spare));
+        scan_reduce_kernel<uint8_t><<<(unsigned)chunks, kScanThreads, 0, stream>>>(keep, total, chunk_count);
         ADJ_TRY(cudaGetLastError());
     }
-    ADJ_TRY(exclusive_scan<uint32_t>(keep, total, pos, scratch, stream));
-    int64_t last_pos = 0;
-    uint32_t last_keep = 0;
+    ADJ_TRY(exclusive_scan<int64_t>(chunk_count, chunks, chunk_base, scratch, stream));
+    int64_t last_base = 0, last_count = 0;
     int h_bad = 0;
-    ADJ_TRY(cudaMemcpyAsync(&last_pos, pos + total - 1, sizeof(int64_t), cudaMemcpyDeviceToHost, stream));
-    ADJ_TRY(cudaMemcpyAsync(&last_keep, keep + total - 1, sizeof(uint32_t), cudaMemcpyDeviceToHost, stream));
+    ADJ_TRY(cudaMemcpyAsync(&last_base, chunk_base + chunks - 1, sizeof(int64_t), cudaMemcpyDeviceToHost, stream));
+    ADJ_TRY(cudaMemcpyAsync(&last_count, chunk_count + chunks - 1, sizeof(int64_t), cudaMemcpyDeviceToHost, stream));
     ADJ_TRY(cudaMemcpyAsync(&h_bad, bad, sizeof(int), cudaMemcpyDeviceToHost, stream));
     ADJ_TRY(cudaStreamSynchronize(stream));
     if (e == cudaSuccess && h_bad) {
         set_error("adjacency_build: an edge endpoint lies outside [0, %lld)", (long long)n);
         status = SGLB200_ERR_INVALID;
     }
-    const int64_t nnz = last_pos + (int64_t)last_keep;
+    const int64_t nnz = last_base + last_count;
     b->nnz = nnz;
     if (e == cudaSuccess && status == SGLB200_OK && nnz > 0) {
         ADJ_TRY(cudaMalloc(&b->row_of, sizeof(int32_t) * nnz));
         ADJ_TRY(cudaMalloc(&b->w2, sizeof(double) * nnz));
-        ADJ_TRY(cudaMalloc(&b->col_sorted, sizeof(uint32_t) * nnz));
-        ADJ_TRY(cudaMalloc(&b->perm, sizeof(uint32_t) * nnz));
         ADJ_TRY(cudaMalloc(&col_a, sizeof(uint32_t) * nnz));
         ADJ_TRY(cudaMalloc(&perm_a, sizeof(uint32_t) * nnz));
+        if (e == cudaSuccess) {
+            compact_kernel<<<(unsigned)chunks, kScanThreads, 0, stream>>>(keys, keep, chunk_base, reinterpret_cast<const double *>(spare), total, col_bits,
+                                                                        b->row_of, col_a, perm_a, b->w2);
+            ADJ_TRY(cudaGetLastError());
+        }
+        // the sort buffers of the first phase are dead: release them before the transpose allocates its own (cudaFree waits
+        // for the kernels above)
+        cudaFree(keys_a);
+        cudaFree(keys_b);
+        cudaFree(vals_a);
+        cudaFree(vals_b);
+        cudaFree(keep);
+        keys_a = keys_b = nullptr;
+        vals_a = vals_b = nullptr;
+        keep = nullptr;
+        ADJ_TRY(cudaMalloc(&b->col_sorted, sizeof(uint32_t) * nnz));
+        ADJ_TRY(cudaMalloc(&b->perm, sizeof(uint32_t) * nnz));
         ADJ_TRY(cudaMalloc(&b->deg, sizeof(double) * n));
         ADJ_TRY(cudaMalloc(&row_ptr, sizeof(int64_t) * (n + 1)));
         if (e == cudaSuccess) {
-            compact_kernel<<<grid_for(total), 256, 0, stream>>>(keys, keep, pos, reinterpret_cast<const double *>(spare), total, col_bits, b->row_of,
-                                                                col_a, perm_a, b->w2);
             lower_bounds_kernel<int32_t><<<grid_for(n + 1), 256, 0, stream>>>(b->row_of, nnz, n, row_ptr);
             row_degree_kernel<<<grid_for(n), 256, 0, stream>>>(row_ptr, b->w2, n, b->deg);
             ADJ_TRY(cudaGetLastError());
@@ -487,7 +518,8 @@ extern "C" int sglb200_adjacency_build(sglb200_adj_builder **out, int64_t n, int
     cudaFree(vals_a);
     cudaFree(vals_b);
     cudaFree(keep);
-    cudaFree(pos);
+    cudaFree(chunk_count);
+    cudaFree(chunk_base);
     cudaFree(scratch);
     cudaFree(col_a);
     cudaFree(perm_a);

@@ -59,6 +59,10 @@ def adjacency_structure_native(rows: torch.Tensor, cols: torch.Tensor, n: int, w
     lib = _lib.load()
     h, nnz = c_void_p(), c_int64(0)
     with torch.cuda.device(dev):
+        # the builder allocates with cudaMalloc, outside torch's pool: hand cached blocks back when it would not fit otherwise
+        need = 56 * (int(rows.numel()) + int(n))
+        if torch.cuda.mem_get_info()[0] < need:
+            torch.cuda.empty_cache()
         check(lib.sglb200_adjacency_build(byref(h), int(n), int(rows.numel()), c_void_p(rows.data_ptr()),
                                           c_void_p(cols.data_ptr()), None if w is None else c_void_p(w.data_ptr()), 1,
                                           byref(nnz), _stream_ptr()), "adjacency_build")
