@@ -147,7 +147,8 @@ def test_iterate_learnable_matches_reference(message_golden):
 @pytest.mark.parametrize("path", golden_graph_files(), ids=lambda p: os.path.basename(p)[6:-4])
 @pytest.mark.parametrize("tag,kind,r,alpha", GRAPH_TAGS)
 def test_device_builder_passes_match_reference(path, tag, kind, r, alpha):
-    """graph_build.normalized_adjacency_device (torch sort / segment passes; run here on CPU tensors) must reproduce
+    """graph_build.normalized_adjacency_device, engine="torch" (the sort / segment passes the CUDA builder is cross-checked
+    against on the GPU; run here on CPU tensors, where it also exercises degree_powers' integer-degree table) must reproduce
     the reference's CSR structure bit-exactly and, with the float64 value formula of sglb200_normalize_values
     restated in numpy, its float64 values."""
     from sgl_b200.graph_build import normalized_adjacency_device
@@ -155,7 +156,7 @@ def test_device_builder_passes_match_reference(path, tag, kind, r, alpha):
     coo = _scipy_adj(adj).tocoo()
     parts = normalized_adjacency_device(torch.from_numpy(coo.row.astype(np.int64)),
                                         torch.from_numpy(coo.col.astype(np.int64)), adj.shape[0],
-                                        torch.from_numpy(coo.data.astype(np.float32)), r=r, alpha=alpha)
+                                        torch.from_numpy(coo.data.astype(np.float32)), r=r, alpha=alpha, engine="torch")
     assert np.array_equal(parts["indptr"].numpy(), z[tag + "_norm_indptr"])
     assert np.array_equal(parts["indices"].numpy(), z[tag + "_norm_indices"])
     rows = np.repeat(np.arange(adj.shape[0]), np.diff(parts["indptr"].numpy()))
@@ -221,3 +222,42 @@ def test_custom_homo_layout_round_trip(tmp_path):
     assert np.array_equal(got["train_idx"], np.arange(10)) and got["val_idx"] is None
     with pytest.raises(ValueError):
         io.read_custom_homo(str(tmp_path), "missing", num_node=5)
+
+
+def test_degree_powers_table_equals_numpy_pow_on_the_vector():
+    """graph_build.degree_powers: integer degree vectors go through a numpy pow table of the distinct values (the vector never
+    leaves the device); the result must be the same float64 bits as numpy's pow applied to the vector itself, inf -> 0
+    (reference utils.py:79-85).  Non-integer vectors take the vector path."""
+    from sgl_b200.graph_build import degree_powers
+    rng = np.random.default_rng(3)
+    for r in (0.5, 0.3, 0.0, 1.0):
+        deg = rng.integers(0, 5000, 20000).astype(np.float64)
+        deg[:5] = [0.0, 1.0, 2.0, 4999.0, 0.0]
+        with np.errstate(divide="ignore", invalid="ignore"):
+            dl, dr = np.power(deg, r - 1), np.power(deg, -r)
+        dl[np.isinf(dl)] = 0.0
+        dr[np.isinf(dr)] = 0.0
+        got_l, got_r = degree_powers(torch.from_numpy(deg), r)
+        assert np.array_equal(got_l.numpy(), dl) and np.array_equal(got_r.numpy(), dr)
+        frac = deg + rng.random(deg.size)
+        with np.errstate(divide="ignore", invalid="ignore"):
+            fl, fr = np.power(frac, r - 1), np.power(frac, -r)
+        got_l, got_r = degree_powers(torch.from_numpy(frac), r)
+        assert np.array_equal(got_l.numpy(), fl) and np.array_equal(got_r.numpy(), fr)
+
+
+def test_feature_split_column_blocks_and_padded_slabs():
+    from sgl_b200.dist import FeatureSplitOperator as F
+    assert F.column_bounds(100, 8).tolist() == [0, 12, 24, 36, 48, 60, 72, 84, 100]
+    assert F.column_bounds(128, 8).tolist() == list(range(0, 129, 16))
+    assert F.column_bounds(7, 4).tolist()[-1] == 7 and F.column_bounds(7, 4).tolist()[0] == 0
+    for w, ld in ((12, 16), (16, 16), (24, 32), (52, 64), (64, 64), (100, 100), (128, 128)):
+        slab = F.block_slab(10, w, "cpu")
+        assert slab.shape == (10, w) and slab.stride(0) == ld and slab.stride(1) == 1
+    # world = 1 operator on CPU tensors with a caller-supplied hop: propagate keeps dense slabs off the GPU
+    a = sp.random(30, 30, 0.2, format="csr", dtype=np.float32, random_state=0)
+    at = torch.from_numpy(a.toarray())
+    fs = F(world=1, rank=0, local_hop=lambda x, out: out.copy_(at @ x))
+    hops = fs.propagate(torch.ones(30, 12), 2)
+    assert torch.allclose(hops[2], at @ (at @ torch.ones(30, 12)))
+    assert F.row_bounds(10, 4).tolist() == [0, 2, 5, 7, 10]
