@@ -631,8 +631,8 @@ static cudaError_t launch_windowed(Kern kern, const SpmmParams &p, dim3 grid, cu
     return cudaLaunchKernelEx(&cfg, kern, p, (const int32_t *)nullptr);
 }
 
-static const int32_t *g_cold_tags = nullptr;   // likewise: the cold-tagged column stream (SGLB200_COLD_HINT)
-static const int32_t *g_flat_tags = nullptr;   // set by spmm_launch_ex for the duration of one launch (host, single thread per handle)
+static thread_local const int32_t *g_cold_tags = nullptr;   // likewise: the cold-tagged column stream (SGLB200_COLD_HINT)
+static thread_local const int32_t *g_flat_tags = nullptr;   // set by spmm_launch_ex for the duration of one launch (host, single thread per handle)
 
 template <int VEC, int VPL, int U, int MINB, int PIPE = 1>
 static cudaError_t launch_flat(const SpmmParams &p, bool accum, dim3 grid, cudaStream_t stream)

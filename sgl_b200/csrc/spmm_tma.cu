@@ -338,13 +338,15 @@ cudaError_t spmm_tma_launch(const sglb200_graph *g, const SpmmParams &p, cudaStr
     if (blocks > needed) blocks = needed;
     const int64_t total_warps = blocks * kWarpsPerBlock;
     const bool unitw = p.vals == nullptr;
+    int dev_slot = 0;
+    if (cudaGetDevice(&dev_slot) != cudaSuccess || dev_slot < 0 || dev_slot >= 64) dev_slot = 0;
 #define TMA_GO(E, W)                                                                                                   \
     do {                                                                                                               \
-        static int attr_bytes = 0;                                                                                     \
-        if (attr_bytes < cta_bytes) {                                                                                  \
+        static int attr_bytes[64] = {0}; /* per device: function attributes belong to the device's context */          \
+        if (attr_bytes[dev_slot] < cta_bytes) {                                                                        \
             cudaError_t e = cudaFuncSetAttribute(spmm_tma_kernel<E, W>, cudaFuncAttributeMaxDynamicSharedMemorySize, cta_bytes); \
             if (e != cudaSuccess) return e;                                                                            \
-            attr_bytes = cta_bytes;                                                                                    \
+            attr_bytes[dev_slot] = cta_bytes;                                                                          \
         }                                                                                                              \
         spmm_tma_kernel<E, W><<<(unsigned)blocks, kWarpsPerBlock * 32, cta_bytes, stream>>>(                           \
             map, p, reinterpret_cast<const uint32_t *>(g->idx_tag), blk_bytes, warp_bytes, total_warps);               \
