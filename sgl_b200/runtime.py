@@ -129,9 +129,10 @@ class CsrOperator:
         """vals[i,j] = fl32((1-alpha) * ((w*dL[i])*dR[j]) + alpha*[i==j]) in float64 on the device (a4)."""
         if isinstance(raw_w, torch.Tensor) and raw_w.is_cuda:
             ts = [t.to(device=raw_w.device, dtype=torch.float64).contiguous() for t in (raw_w, d_left, d_right)]
-            check(_lib.load().sglb200_normalize_values(self._h, *[c_void_p(t.data_ptr()) for t in ts], float(alpha),
-                                                       int(apply_ppr), _lib.DEVICE, _stream_ptr()), "normalize_values")
-            torch.cuda.current_stream().synchronize()
+            with torch.cuda.device(self.device):
+                check(_lib.load().sglb200_normalize_values(self._h, *[c_void_p(t.data_ptr()) for t in ts], float(alpha),
+                                                           int(apply_ppr), _lib.DEVICE, _stream_ptr()), "normalize_values")
+                torch.cuda.current_stream().synchronize()
             return
         arrs = [np.ascontiguousarray(a, dtype=np.float64) for a in (raw_w, d_left, d_right)]
         check(_lib.load().sglb200_normalize_values(self._h, *[c_void_p(a.ctypes.data) for a in arrs], float(alpha),
@@ -155,8 +156,9 @@ class CsrOperator:
             raise ValueError("spmm: bad out tensor")
         ldx = int(x.stride(0)) if x.shape[0] > 1 else max(d, int(x.stride(0)))
         ldy = int(out.stride(0)) if out.shape[0] > 1 else max(d, int(out.stride(0)))
-        check(_lib.load().sglb200_spmm(self._h, c_void_p(x.data_ptr()), ldx, c_void_p(out.data_ptr()), ldy, d,
-                                       _MODES[mode], int(accumulate), _stream_ptr()), "spmm")
+        with torch.cuda.device(self.device):      # the handle lives on self.device; launch there, on its current stream
+            check(_lib.load().sglb200_spmm(self._h, c_void_p(x.data_ptr()), ldx, c_void_p(out.data_ptr()), ldy, d,
+                                           _MODES[mode], int(accumulate), _stream_ptr()), "spmm")
         return out
 
     def spmm_axpby(self, x: torch.Tensor, alpha: float, res: Optional[torch.Tensor] = None, clamp=None, mode="fast",
@@ -187,8 +189,9 @@ class CsrOperator:
         d = int(x.shape[1])
         ldx = int(x.stride(0)) if x.shape[0] > 1 else d
         ldy = int(out.stride(0)) if out.shape[0] > 1 else d
-        check(_lib.load().sglb200_spmm_tiles(self._h, c_void_p(x.data_ptr()), ldx, c_void_p(out.data_ptr()), ldy, d,
-                                             _MODES[mode], int(tile_begin), int(tile_end), _stream_ptr()), "spmm_tiles")
+        with torch.cuda.device(self.device):
+            check(_lib.load().sglb200_spmm_tiles(self._h, c_void_p(x.data_ptr()), ldx, c_void_p(out.data_ptr()), ldy, d,
+                                                 _MODES[mode], int(tile_begin), int(tile_end), _stream_ptr()), "spmm_tiles")
         return out
 
     # ---- K hops, device resident ------------------------------------------------------------------------------
@@ -213,8 +216,9 @@ class CsrOperator:
             hops = [x] + [torch.empty_like(x) for _ in range(K)]
             ld = d
         if n and d and K:
-            check(_lib.load().sglb200_propagate(self._h, _lib.ptr_array([h.data_ptr() for h in hops]), ld, d, K,
-                                                _MODES[mode], _stream_ptr()), "propagate")
+            with torch.cuda.device(self.device):
+                check(_lib.load().sglb200_propagate(self._h, _lib.ptr_array([h.data_ptr() for h in hops]), ld, d, K,
+                                                    _MODES[mode], _stream_ptr()), "propagate")
         return hops
 
     # ---- K hops + degree normalisation + cross-hop aggregation in one pass per hop -----------------------------
@@ -286,8 +290,9 @@ class CsrOperator:
                 outs.append(None)
         if K and n and d:
             ptrs = _lib.ptr_array([None if o is None else o.data_ptr() for o in outs])
-            check(_lib.load().sglb200_propagate_host(self._h, c_void_p(x.ctypes.data), ptrs, int(d), K, _MODES[mode]),
-                  "propagate_host")
+            with torch.cuda.device(self.device):
+                check(_lib.load().sglb200_propagate_host(self._h, c_void_p(x.ctypes.data), ptrs, int(d), K, _MODES[mode]),
+                      "propagate_host")
         return outs
 
 
